@@ -1,0 +1,16 @@
+// csrc/ref_inst.cu -- one translation unit per level count (compiled with -DSSPYR_NL=3..8, in
+// parallel): instantiates the fused REF kernel of ref_kernel.cuh for every pixel type / rows-per-thread.
+#include "ref_kernel.cuh"
+
+#ifndef SSPYR_NL
+#error "compile with -DSSPYR_NL=<levels>"
+#endif
+#define SSPYR_CAT2(a, b) a##b
+#define SSPYR_CAT(a, b) SSPYR_CAT2(a, b)
+
+namespace sspyr {
+cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, dim3 grid, int block,
+                                               cudaStream_t st) {
+    return launch_pix<SSPYR_NL>(P, pix, rpt, grid, block, st);
+}
+}  // namespace sspyr

@@ -1,0 +1,88 @@
+// csrc/ref_launch.cu -- host side of the fused REF build: fills the kernel parameter block from the
+// handle and picks the instantiation (ref_inst.cu) for the handle's level count.
+#include "sspyr_internal.h"
+
+namespace sspyr {
+
+#define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, dim3, int, cudaStream_t);
+SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
+#undef SSPYR_DECL
+
+namespace {
+
+int sm_count(int device) {
+    static int cached[64] = {0};
+    if (device >= 0 && device < 64 && cached[device]) return cached[device];
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    if (device >= 0 && device < 64) cached[device] = n;
+    return n;
+}
+
+}  // namespace
+
+// Enqueue the fused REF build of frame slots first .. first+count-1 (one launch when the slots are the
+// handle's own contiguous buffers; one launch per frame when a slot reads an external device image).
+cudaError_t launch_ref(const sspyr_ctx* h, int first, int count, int outputs, int* launches) {
+    const int frames = h->cfg.frames;
+    int done = 0;
+    while (done < count) {
+        const int f0 = (first + done) % frames;
+        int n = 1;
+        if (!h->ext_in[f0])
+            while (done + n < count && f0 + n < frames && !h->ext_in[f0 + n]) ++n;
+
+        RefParams P{};
+        size_t pitch_bytes = 0;
+        P.img = frame_input(h, f0, &pitch_bytes);
+        P.img_frame_stride = h->in_frame_bytes;
+        P.out_frame_stride = h->frame_floats;
+        P.img_pitch = (int)(pitch_bytes / h->elem_bytes);
+        P.H = h->cfg.height;
+        P.W = h->cfg.width;
+        P.octaves = h->octaves;
+        P.outputs = outputs;
+        for (int o = 0; o < h->octaves; ++o) {
+            const OctGeom& g = h->oct[o];
+            P.oct[o].base = frame_out(h, f0) + g.off;
+            P.oct[o].fw = h->d_tables + g.fw_off;
+            P.oct[o].fh = h->d_tables + g.fh_off;
+            P.oct[o].H = g.H;
+            P.oct[o].W = g.W;
+            P.oct[o].pitch = g.pitch;
+            P.oct[o].plane = g.plane;
+        }
+
+        int rpt = h->tune.rows_per_thread;
+        if (rpt <= 0) rpt = 4;
+        rpt = rpt >= 8 ? 8 : rpt >= 4 ? 4 : rpt >= 2 ? 2 : 1;
+        int block = h->tune.block > 0 ? h->tune.block : 256;
+        block = block > 256 ? 256 : (block < 32 ? 32 : (block / 32) * 32);
+        const long long items = (long long)((P.W + 3) >> 2) * ((P.H + rpt - 1) / rpt);
+        long long gx = (items + block - 1) / block;
+        if (h->tune.grid_mult > 0) {
+            const long long cap = (long long)sm_count(h->device) * h->tune.grid_mult;
+            if (gx > cap) gx = cap;
+        }
+        if (gx < 1) gx = 1;
+        if (gx > 0x7fffffffLL) gx = 0x7fffffffLL;
+        const dim3 grid((unsigned)gx, (unsigned)n, 1);
+
+        cudaError_t e;
+        switch (h->nl) {
+            case 3: e = launch_ref_nl3(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 4: e = launch_ref_nl4(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 5: e = launch_ref_nl5(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            default: return cudaErrorInvalidValue;   // S in 0..5 (create() rejects the rest for REF mode)
+        }
+        if (e != cudaSuccess) return e;
+        ++*launches;
+        done += n;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace sspyr

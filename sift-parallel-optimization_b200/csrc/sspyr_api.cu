@@ -1,0 +1,519 @@
+// csrc/sspyr_api.cu -- the extern "C" boundary declared in include/sspyr.h: host state, window/tap
+// tables, buffer layout, copies.  All compute is in ref_kernels.cu / conv_kernels.cu; there is no CPU
+// implementation of the hot path anywhere in this library.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "sspyr_internal.h"
+
+using namespace sspyr;
+
+namespace {
+
+thread_local std::string g_create_err;
+
+int fail(sspyr_ctx* h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+int fail_cuda(sspyr_ctx* h, cudaError_t e, const char* what) {
+    cudaGetLastError();   // clear sticky-less error state
+    return fail(h, SSPYR_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(h, call)                                            \
+    do {                                                       \
+        cudaError_t e_ = (call);                               \
+        if (e_ != cudaSuccess) return fail_cuda(h, e_, #call); \
+    } while (0)
+
+inline size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// The reference's mistyped pi and its sigma, narrowed from double literals exactly as the header does
+// (GuassDePyramid.h:7-8).
+const float kPiRef = 3.1414926;
+const float kSigmaRef = 2.0;
+
+// K1 -- window of one (axis, octave, level): GuassDePyramid.h:107-121.  Same expression, same float
+// types, same libm (expf/sqrtf are what `exp`/`sqrt` resolve to there), so the table is bit-identical
+// to the one the header builds; nvcc's host pass is told not to contract (-ffp-contract=off).
+void ref_window(int axis_len, int o, int s, float sigma0, float* f) {
+    float len = (float)axis_len;                 // :107
+    for (int t = o; t != 0; --t) len /= 2;       // :109-112  (float halving: 1080 -> 67.5 at o=4)
+    const int mylen = (int)len;                  // :114
+    len = (len - 1) / 2;                         // :115
+    const float sig = sigma0 / (s + 1);          // :118
+    for (int i = 0; i < mylen; ++i)              // :119-121
+        f[i] = expf(-(i - len) * (i - len) / (2 * sig * sig)) / (sig * sqrtf(2 * kPiRef));
+}
+
+int octaves_all(int h, int w) {                  // GuassDePyramid.h:48-53 on the short side
+    int len = h < w ? h : w, x = 0;
+    while (len) { x++; len /= 2; }
+    return x;
+}
+
+// CONV tap schedule (DESIGN.md "CONV mode"): incremental sigma of level s and its normalised taps.
+double conv_sigma_inc(int s, int S, float sigma0, float sigma_in) {
+    if (s == 0) {
+        double d = (double)sigma0 * sigma0 - (double)sigma_in * sigma_in;
+        if (d < 0.01) d = 0.01;
+        return std::sqrt(d);
+    }
+    const double k = std::pow(2.0, 1.0 / (double)S);
+    const double prev = (double)sigma0 * std::pow(k, (double)(s - 1));
+    const double tot = prev * k;
+    return std::sqrt(tot * tot - prev * prev);
+}
+
+int conv_make_taps(double si, float radius_sigmas, std::vector<float>& taps) {
+    int R = (int)std::ceil((double)radius_sigmas * si);
+    if (R < 1) R = 1;
+    double sum = 0.0;
+    for (int k = -R; k <= R; ++k) sum += std::exp(-(double)k * k / (2.0 * si * si));
+    taps.resize(2 * R + 1);
+    for (int k = -R; k <= R; ++k) taps[k + R] = (float)(std::exp(-(double)k * k / (2.0 * si * si)) / sum);
+    return R;
+}
+
+bool valid_frame(const sspyr_ctx* h, int frame) { return frame >= 0 && frame < h->cfg.frames; }
+
+int plane_lookup(sspyr_ctx* h, int octave, int level, int kind, int* index) {
+    if (octave < 0 || octave >= h->octaves) return fail(h, SSPYR_ERR_ARG, "octave out of range");
+    const int nl = h->nl;
+    int lim = kind == SSPYR_KIND_DOG ? nl - 1 : nl;
+    if (kind != SSPYR_KIND_GAUSS && kind != SSPYR_KIND_DOG && kind != SSPYR_KIND_INPLACE)
+        return fail(h, SSPYR_ERR_ARG, "bad plane kind");
+    if (level < 0 || level >= lim) return fail(h, SSPYR_ERR_ARG, "level out of range");
+    const int out = h->cfg.outputs;
+    bool have;
+    if (kind == SSPYR_KIND_GAUSS) have = (out & SSPYR_OUT_GAUSS) || (level == nl - 1 && (out & SSPYR_OUT_GAUSS_TOP));
+    else if (kind == SSPYR_KIND_DOG) have = out & SSPYR_OUT_DOG;
+    else have = level == nl - 1 ? (out & (SSPYR_OUT_GAUSS | SSPYR_OUT_GAUSS_TOP)) : (out & SSPYR_OUT_DOG);
+    if (!have) return fail(h, SSPYR_ERR_STATE, "that plane is not among the configured outputs");
+    *index = plane_index(nl, kind, level);
+    return SSPYR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sspyr_version(void) { return SSPYR_VERSION; }
+
+int sspyr_default_config(sspyr_config* cfg) {
+    if (!cfg) return SSPYR_ERR_ARG;
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->S = 3;
+    cfg->mode = SSPYR_MODE_REF;
+    cfg->outputs = SSPYR_OUT_ALL;
+    cfg->pixel_type = SSPYR_PIXEL_I32;
+    cfg->frames = 1;
+    cfg->device = -1;
+    cfg->sigma_in = 0.5f;
+    cfg->radius_sigmas = 3.0f;
+    cfg->extrema_thresh = 0.0f;
+    return SSPYR_OK;
+}
+
+int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
+    if (!cfg_in || !out) return fail(nullptr, SSPYR_ERR_ARG, "null argument");
+    *out = nullptr;
+    sspyr_config cfg = *cfg_in;
+    if (cfg.height < 1 || cfg.width < 1) return fail(nullptr, SSPYR_ERR_ARG, "height and width must be >= 1");
+    if (cfg.S < 0 || cfg.S + 3 > SSPYR_MAX_LEVELS) return fail(nullptr, SSPYR_ERR_ARG, "S out of range");
+    if (cfg.mode != SSPYR_MODE_REF && cfg.mode != SSPYR_MODE_CONV) return fail(nullptr, SSPYR_ERR_ARG, "bad mode");
+    if (cfg.mode == SSPYR_MODE_REF && cfg.S > 5) return fail(nullptr, SSPYR_ERR_UNSUPPORTED, "REF mode supports S <= 5");
+    if (cfg.mode == SSPYR_MODE_CONV && cfg.S < 1) return fail(nullptr, SSPYR_ERR_ARG, "CONV mode needs S >= 1");
+    if (cfg.pixel_type < 0 || cfg.pixel_type > SSPYR_PIXEL_U8) return fail(nullptr, SSPYR_ERR_ARG, "bad pixel type");
+    if (cfg.frames < 1) cfg.frames = 1;
+    if (cfg.outputs == 0) cfg.outputs = SSPYR_OUT_ALL;
+    if (cfg.full_height <= 0) cfg.full_height = cfg.height;
+    if (cfg.band_row0 < 0 || cfg.band_row0 + cfg.height > cfg.full_height)
+        return fail(nullptr, SSPYR_ERR_ARG, "row band outside the full image");
+    if (cfg.sigma0 <= 0.0f) cfg.sigma0 = cfg.mode == SSPYR_MODE_REF ? kSigmaRef : 1.6f;
+    if (cfg.sigma_in < 0.0f) cfg.sigma_in = 0.5f;
+    if (cfg.radius_sigmas <= 0.0f) cfg.radius_sigmas = 3.0f;
+    const int all = octaves_all(cfg.full_height, cfg.width);
+    if (cfg.octaves <= 0) cfg.octaves = all;
+    if (cfg.octaves > all || cfg.octaves > SSPYR_MAX_OCTAVES)
+        return fail(nullptr, SSPYR_ERR_ARG, "more octaves than floor(log2(min(H,W)))+1");
+    const bool banded = cfg.full_height != cfg.height;
+    if (banded) {
+        const int align = 1 << (cfg.octaves - 1);
+        if (cfg.band_row0 % align) return fail(nullptr, SSPYR_ERR_ARG, "band_row0 must be a multiple of 2^(octaves-1)");
+        if (cfg.band_row0 + cfg.height != cfg.full_height && cfg.height % align)
+            return fail(nullptr, SSPYR_ERR_ARG, "interior band heights must be multiples of 2^(octaves-1)");
+    }
+    if ((cfg.outputs & SSPYR_OUT_EXTREMA) && !(cfg.outputs & SSPYR_OUT_DOG))
+        return fail(nullptr, SSPYR_ERR_ARG, "SSPYR_OUT_EXTREMA needs SSPYR_OUT_DOG");
+    if (cfg.mode == SSPYR_MODE_CONV) cfg.outputs |= SSPYR_OUT_GAUSS;   // the blur chain reads its own levels
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, SSPYR_ERR_CUDA,
+                    std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+    }
+    sspyr_ctx* h = new (std::nothrow) sspyr_ctx();
+    if (!h) return fail(nullptr, SSPYR_ERR_NOMEM, "host allocation failed");
+    auto bail = [&](int code, const std::string& msg) {
+        g_create_err = msg;
+        sspyr_destroy(h);
+        return code;
+    };
+    if (cfg.device < 0) {
+        if ((e = cudaGetDevice(&cfg.device)) != cudaSuccess) return bail(SSPYR_ERR_CUDA, cudaGetErrorString(e));
+    } else if (cfg.device >= ndev) {
+        return bail(SSPYR_ERR_ARG, "device ordinal out of range");
+    }
+    if ((e = cudaSetDevice(cfg.device)) != cudaSuccess) return bail(SSPYR_ERR_CUDA, cudaGetErrorString(e));
+    h->cfg = cfg;
+    h->device = cfg.device;
+    h->octaves = cfg.octaves;
+    h->nl = cfg.S + 3;
+    h->elem_bytes = cfg.pixel_type == SSPYR_PIXEL_U8 ? 1 : 4;
+    h->ext_in.assign(cfg.frames, nullptr);
+    h->ext_pitch.assign(cfg.frames, 0);
+    h->built.assign(cfg.frames, 0);
+
+    // ---- output layout ----
+    const int nl = h->nl, S = cfg.S;
+    size_t off = 0, tab = 0, ext = 0;
+    for (int o = 0; o < h->octaves; ++o) {
+        OctGeom& g = h->oct[o];
+        g.H = cfg.height >> o;
+        g.W = cfg.width >> o;
+        if (g.H < 1 || g.W < 1) {
+            // a short last band can run out of rows before the full image does
+            return bail(SSPYR_ERR_ARG, "band too short for the requested octave count");
+        }
+        g.pitch = (int)round_up((size_t)g.W, 32);
+        g.plane = (size_t)g.H * g.pitch;
+        g.off = off;
+        off += (size_t)(2 * nl - 1) * g.plane;
+        g.ext_off = ext;
+        ext += (size_t)(S > 0 ? S : 0) * g.plane;
+        if (cfg.mode == SSPYR_MODE_REF) {
+            g.fw_off = tab;
+            tab += (size_t)nl * g.pitch;
+            g.fh_off = tab;
+            tab += round_up((size_t)nl * g.H, 32);
+        }
+    }
+    h->frame_floats = round_up(off, 64);
+    h->ext_frame_bytes = round_up(ext, 256);
+
+    // ---- tables ----
+    if (cfg.mode == SSPYR_MODE_REF) {
+        h->h_tables.assign(tab, 0.0f);
+        std::vector<float> full((size_t)(cfg.full_height > cfg.width ? cfg.full_height : cfg.width) + 1);
+        for (int o = 0; o < h->octaves; ++o) {
+            const OctGeom& g = h->oct[o];
+            const int r0 = cfg.band_row0 >> o;
+            for (int s = 0; s < nl; ++s) {
+                ref_window(cfg.width, o, s, cfg.sigma0, full.data());
+                std::memcpy(&h->h_tables[g.fw_off + (size_t)s * g.pitch], full.data(), sizeof(float) * g.W);
+                ref_window(cfg.full_height, o, s, cfg.sigma0, full.data());
+                std::memcpy(&h->h_tables[g.fh_off + (size_t)s * g.H], full.data() + r0, sizeof(float) * g.H);
+            }
+        }
+    } else {
+        h->conv.resize(nl);
+        std::vector<float> taps;
+        for (int s = 0; s < nl; ++s) {
+            const int R = conv_make_taps(conv_sigma_inc(s, S, cfg.sigma0, cfg.sigma_in), cfg.radius_sigmas, taps);
+            if (R > 32) return bail(SSPYR_ERR_UNSUPPORTED, "CONV tap radius > 32 (lower sigma0, S or radius_sigmas)");
+            h->conv[s].radius = R;
+            h->conv[s].taps_off = h->h_tables.size();
+            h->h_tables.insert(h->h_tables.end(), taps.begin(), taps.end());
+            h->h_tables.resize(round_up(h->h_tables.size(), 32), 0.0f);
+        }
+    }
+
+    // ---- device memory ----
+    const size_t in_row = (size_t)cfg.width * h->elem_bytes;
+    h->in_pitch_bytes = round_up(in_row, 128);
+    h->in_frame_bytes = round_up(h->in_pitch_bytes * cfg.height + 128, 256);
+    auto dmalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256); };
+    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * h->frame_floats * cfg.frames)) != cudaSuccess ||
+        (e = dmalloc((void**)&h->d_in, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
+        (e = dmalloc((void**)&h->d_tables, sizeof(float) * h->h_tables.size())) != cudaSuccess) {
+        cudaGetLastError();
+        return bail(e == cudaErrorMemoryAllocation ? SSPYR_ERR_NOMEM : SSPYR_ERR_CUDA,
+                    std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    if (cfg.outputs & SSPYR_OUT_EXTREMA) {
+        if ((e = dmalloc((void**)&h->d_ext, h->ext_frame_bytes * cfg.frames)) != cudaSuccess) {
+            cudaGetLastError();
+            return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+    }
+    if ((e = cudaMemcpy(h->d_tables, h->h_tables.data(), sizeof(float) * h->h_tables.size(),
+                        cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemset(h->d_in, 0, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
+        (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess)
+        return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    *out = h;
+    return SSPYR_OK;
+}
+
+int sspyr_destroy(sspyr_handle h) {
+    if (!h) return SSPYR_OK;
+    cudaSetDevice(h->device);
+    if (h->d_out) cudaFree(h->d_out);
+    if (h->d_ext) cudaFree(h->d_ext);
+    if (h->d_in) cudaFree(h->d_in);
+    if (h->d_tables) cudaFree(h->d_tables);
+    if (h->d_halo) cudaFree(h->d_halo);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    cudaGetLastError();
+    delete h;
+    return SSPYR_OK;
+}
+
+const char* sspyr_last_error(sspyr_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int sspyr_num_octaves(sspyr_handle h) { return h ? h->octaves : SSPYR_ERR_ARG; }
+int sspyr_num_levels(sspyr_handle h) { return h ? h->nl : SSPYR_ERR_ARG; }
+int sspyr_num_dogs(sspyr_handle h) { return h ? h->nl - 1 : SSPYR_ERR_ARG; }
+
+int sspyr_level_dims(sspyr_handle h, int octave, int* rows, int* cols, size_t* pitch_floats) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (octave < 0 || octave >= h->octaves) return fail(h, SSPYR_ERR_ARG, "octave out of range");
+    if (rows) *rows = h->oct[octave].H;
+    if (cols) *cols = h->oct[octave].W;
+    if (pitch_floats) *pitch_floats = (size_t)h->oct[octave].pitch;
+    return SSPYR_OK;
+}
+
+int sspyr_algorithmic_bytes(sspyr_handle h, uint64_t* bytes) {
+    if (!h || !bytes) return SSPYR_ERR_ARG;
+    const int out = h->cfg.outputs, nl = h->nl;
+    int planes = 0;
+    if (out & SSPYR_OUT_GAUSS) planes += nl;
+    else if (out & SSPYR_OUT_GAUSS_TOP) planes += 1;
+    if (out & SSPYR_OUT_DOG) planes += nl - 1;
+    uint64_t px = 0, ext = 0;
+    for (int o = 0; o < h->octaves; ++o) px += (uint64_t)h->oct[o].H * h->oct[o].W;
+    if (out & SSPYR_OUT_EXTREMA) ext = px * (uint64_t)h->cfg.S;
+    *bytes = (uint64_t)h->cfg.height * h->cfg.width * h->elem_bytes + 4ull * planes * px + ext;
+    return SSPYR_OK;
+}
+
+int sspyr_set_stream(sspyr_handle h, void* cuda_stream) {
+    if (!h) return SSPYR_ERR_ARG;
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return SSPYR_OK;
+}
+
+int sspyr_upload(sspyr_handle h, int frame, const void* host, size_t pitch_bytes) {
+    if (!h || !host) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    const size_t row = (size_t)h->cfg.width * h->elem_bytes;
+    if (pitch_bytes == 0) pitch_bytes = row;
+    if (pitch_bytes < row) return fail(h, SSPYR_ERR_ARG, "pitch smaller than a row");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy2DAsync(h->d_in + (size_t)frame * h->in_frame_bytes, h->in_pitch_bytes, host, pitch_bytes,
+                            row, h->cfg.height, cudaMemcpyHostToDevice, h->stream));
+    h->ext_in[frame] = nullptr;
+    h->built[frame] = 0;
+    return SSPYR_OK;
+}
+
+int sspyr_set_input_device(sspyr_handle h, int frame, const void* dev, size_t pitch_bytes) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (dev) {
+        const size_t row = (size_t)h->cfg.width * h->elem_bytes;
+        if (pitch_bytes == 0) pitch_bytes = row;
+        if (pitch_bytes < row || pitch_bytes % 16 || reinterpret_cast<uintptr_t>(dev) % 16)
+            return fail(h, SSPYR_ERR_ARG, "device image must be 16-byte aligned with a pitch that is a multiple of 16 bytes");
+    }
+    h->ext_in[frame] = dev;
+    h->ext_pitch[frame] = pitch_bytes;
+    h->built[frame] = 0;
+    return SSPYR_OK;
+}
+
+int sspyr_build_batch(sspyr_handle h, int first, int count) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, first) || count < 1) return fail(h, SSPYR_ERR_ARG, "bad frame range");
+    CU(h, cudaSetDevice(h->device));
+    int launches = 0;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    cudaError_t e = cudaSuccess;
+    if (h->cfg.mode == SSPYR_MODE_REF) {
+        e = launch_ref(h, first, count, h->cfg.outputs, &launches);
+        for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
+            e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
+    } else {
+        for (int i = 0; i < count && e == cudaSuccess; ++i) {
+            e = launch_conv(h, (first + i) % h->cfg.frames, &launches);
+            if (e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA))
+                e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
+        }
+    }
+    if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->last_launches = launches;
+    for (int i = 0; i < count; ++i) h->built[(first + i) % h->cfg.frames] = 1;
+    return SSPYR_OK;
+}
+
+int sspyr_build(sspyr_handle h, int frame) { return sspyr_build_batch(h, frame, 1); }
+
+int sspyr_build_stage(sspyr_handle h, int frame, int stage) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (stage == SSPYR_STAGE_DOG) return sspyr_build_batch(h, frame, 1);
+    if (stage != SSPYR_STAGE_INIT && stage != SSPYR_STAGE_FILTER) return fail(h, SSPYR_ERR_ARG, "bad stage");
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (h->cfg.mode != SSPYR_MODE_REF) return fail(h, SSPYR_ERR_UNSUPPORTED, "partial stages exist in REF mode only");
+    if (!(h->cfg.outputs & SSPYR_OUT_GAUSS)) return fail(h, SSPYR_ERR_STATE, "partial stages need SSPYR_OUT_GAUSS");
+    CU(h, cudaSetDevice(h->device));
+    int launches = 0;
+    CU(h, cudaEventRecord(h->ev0, h->stream));
+    const int outputs = SSPYR_OUT_GAUSS | (stage == SSPYR_STAGE_INIT ? SSPYR_INT_INIT_ONLY : 0);
+    const cudaError_t e = launch_ref(h, frame, 1, outputs, &launches);
+    if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
+    CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+    h->last_launches = launches;
+    h->built[frame] = 1;
+    return SSPYR_OK;
+}
+
+int sspyr_sync(sspyr_handle h) {
+    if (!h) return SSPYR_ERR_ARG;
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SSPYR_OK;
+}
+
+int sspyr_elapsed_ms(sspyr_handle h, float* ms) {
+    if (!h || !ms) return SSPYR_ERR_ARG;
+    if (!h->timed) return fail(h, SSPYR_ERR_STATE, "no build has been enqueued yet");
+    CU(h, cudaEventSynchronize(h->ev1));
+    CU(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return SSPYR_OK;
+}
+
+int sspyr_last_launches(sspyr_handle h) { return h ? h->last_launches : SSPYR_ERR_ARG; }
+
+int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind, void** ptr) {
+    if (!h || !ptr) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (kind == SSPYR_KIND_EXTREMA) {
+        if (!h->d_ext) return fail(h, SSPYR_ERR_STATE, "extrema output not configured");
+        if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->cfg.S)
+            return fail(h, SSPYR_ERR_ARG, "extrema plane out of range");
+        *ptr = h->d_ext + (size_t)frame * h->ext_frame_bytes + h->oct[octave].ext_off + (size_t)level * h->oct[octave].plane;
+        return SSPYR_OK;
+    }
+    int idx = 0;
+    const int rc = plane_lookup(h, octave, level, kind, &idx);
+    if (rc) return rc;
+    *ptr = frame_out(h, frame) + h->oct[octave].off + (size_t)idx * h->oct[octave].plane;
+    return SSPYR_OK;
+}
+
+int sspyr_download(sspyr_handle h, int frame, int octave, int level, int kind, void* dst, size_t pitch_bytes) {
+    if (!h || !dst) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
+    void* src = nullptr;
+    const int rc = sspyr_device_ptr(h, frame, octave, level, kind, &src);
+    if (rc) return rc;
+    const OctGeom& g = h->oct[octave];
+    const size_t es = kind == SSPYR_KIND_EXTREMA ? 1 : sizeof(float);
+    const size_t row = (size_t)g.W * es;
+    if (pitch_bytes == 0) pitch_bytes = row;
+    if (pitch_bytes < row) return fail(h, SSPYR_ERR_ARG, "pitch smaller than a row");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy2DAsync(dst, pitch_bytes, src, (size_t)g.pitch * es, row, g.H, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return SSPYR_OK;
+}
+
+int sspyr_download_inplace(sspyr_handle h, int frame, float* dst) {
+    if (!h || !dst) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
+    const int out = h->cfg.outputs;
+    if (!(out & SSPYR_OUT_DOG) || !(out & (SSPYR_OUT_GAUSS | SSPYR_OUT_GAUSS_TOP)))
+        return fail(h, SSPYR_ERR_STATE, "in-place layout needs DOG and GAUSS(_TOP) outputs");
+    CU(h, cudaSetDevice(h->device));
+    const int nl = h->nl;
+    for (int o = 0; o < h->octaves; ++o) {
+        const OctGeom& g = h->oct[o];
+        const float* src = frame_out(h, frame) + g.off + (size_t)(nl - 1) * g.plane;   // DoG_0 .. G_{S+2}
+        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, src, sizeof(float) * g.pitch, sizeof(float) * g.W,
+                                (size_t)nl * g.H, cudaMemcpyDeviceToHost, h->stream));
+        dst += (size_t)nl * g.H * g.W;
+    }
+    return SSPYR_OK;
+}
+
+int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
+    if (!h || !dst) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
+    if (!(h->cfg.outputs & SSPYR_OUT_GAUSS)) return fail(h, SSPYR_ERR_STATE, "GAUSS output not configured");
+    CU(h, cudaSetDevice(h->device));
+    const int nl = h->nl;
+    for (int o = 0; o < h->octaves; ++o) {
+        const OctGeom& g = h->oct[o];
+        const float* base = frame_out(h, frame) + g.off;
+        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, base, sizeof(float) * g.pitch, sizeof(float) * g.W,
+                                (size_t)(nl - 1) * g.H, cudaMemcpyDeviceToHost, h->stream));
+        dst += (size_t)(nl - 1) * g.H * g.W;
+        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, base + (size_t)(2 * nl - 2) * g.plane, sizeof(float) * g.pitch,
+                                sizeof(float) * g.W, g.H, cudaMemcpyDeviceToHost, h->stream));
+        dst += (size_t)g.H * g.W;
+    }
+    return SSPYR_OK;
+}
+
+int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* dst, int capacity) {
+    if (!h || !dst) return SSPYR_ERR_ARG;
+    if (h->cfg.mode != SSPYR_MODE_REF) return fail(h, SSPYR_ERR_STATE, "window tables exist in REF mode only");
+    if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl || (axis != 0 && axis != 1))
+        return fail(h, SSPYR_ERR_ARG, "bad table index");
+    const OctGeom& g = h->oct[octave];
+    const int n = axis == 0 ? g.H : g.W;
+    if (capacity < n) return fail(h, SSPYR_ERR_ARG, "destination too small");
+    const size_t off = axis == 0 ? g.fh_off + (size_t)level * g.H : g.fw_off + (size_t)level * g.pitch;
+    // read back from the DEVICE copy: this is what the kernel actually multiplies by
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy(dst, h->d_tables + off, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    return n;
+}
+
+int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* radius) {
+    if (!h || !dst) return SSPYR_ERR_ARG;
+    if (h->cfg.mode != SSPYR_MODE_CONV) return fail(h, SSPYR_ERR_STATE, "taps exist in CONV mode only");
+    if (level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "level out of range");
+    const int R = h->conv[level].radius;
+    if (capacity < 2 * R + 1) return fail(h, SSPYR_ERR_ARG, "destination too small");
+    CU(h, cudaSetDevice(h->device));
+    CU(h, cudaMemcpy(dst, h->d_tables + h->conv[level].taps_off, sizeof(float) * (2 * R + 1), cudaMemcpyDeviceToHost));
+    if (radius) *radius = R;
+    return SSPYR_OK;
+}
+
+int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
+    if (!h || !key) return SSPYR_ERR_ARG;
+    if (!std::strcmp(key, "rows_per_thread")) h->tune.rows_per_thread = value;
+    else if (!std::strcmp(key, "block")) h->tune.block = value;
+    else if (!std::strcmp(key, "grid_mult")) h->tune.grid_mult = value;
+    else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
+    return SSPYR_OK;
+}
+
+}  // extern "C"

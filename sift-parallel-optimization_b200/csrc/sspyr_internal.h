@@ -1,0 +1,116 @@
+// csrc/sspyr_internal.h -- private to libsspyr.so (host state of one handle + kernel launch ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/sspyr.h"
+
+// internal bits or-ed into RefParams::outputs (above the public SSPYR_OUT_* mask)
+#define SSPYR_INT_INIT_ONLY (1 << 16)   // K0 only: G_s = p
+
+namespace sspyr {
+
+// ---- per-octave geometry of one frame slot -------------------------------------------------------
+struct OctGeom {
+    int H = 0, W = 0;          // H>>o, W>>o                      (GuassDePyramid.h:66)
+    int pitch = 0;             // floats, multiple of 32 (128-byte rows)
+    size_t plane = 0;          // H * pitch floats
+    size_t off = 0;            // float offset of this octave inside a frame slot
+    size_t fw_off = 0;         // REF: float offset of the column-window table [NL][pitch] in d_tables
+    size_t fh_off = 0;         // REF: float offset of the row-window table    [NL][H]
+    size_t ext_off = 0;        // byte offset of the extrema planes [S][H][pitch] inside an extrema slot
+};
+
+// ---- kernel parameter blocks (passed __grid_constant__) ---------------------------------------------
+struct RefOct {
+    float* base;               // [G_0..G_{S+1} | DoG_0..DoG_{S+1} | G_{S+2}] of frame 0 of the launch
+    const float* fw;           // [NL][pitch]
+    const float* fh;           // [NL][H]
+    int H, W, pitch;
+    unsigned long long plane;
+};
+
+struct RefParams {
+    const void* img;           // frame 0 of the launch
+    unsigned long long img_frame_stride;   // bytes between consecutive frames (batched launch)
+    unsigned long long out_frame_stride;   // floats between consecutive frame slots
+    int img_pitch;             // elements between input rows
+    int H, W;                  // input rows (this band) / columns
+    int octaves;
+    int outputs;               // SSPYR_OUT_* mask
+    RefOct oct[SSPYR_MAX_OCTAVES];
+};
+
+struct Tuning {
+    int rows_per_thread = 0;   // 0 = heuristic
+    int block = 0;
+    int grid_mult = 0;         // CTAs per SM for the grid-stride launch; 0 = one CTA per work chunk
+};
+
+// CONV mode: one level step (see conv_kernels.cu)
+struct ConvLevel {
+    int radius = 0;
+    size_t taps_off = 0;       // float offset in d_tables of taps[2R+1]
+};
+
+}  // namespace sspyr
+
+// ---- the handle -----------------------------------------------------------------------------------
+struct sspyr_ctx {
+    sspyr_config cfg{};
+    int octaves = 0, nl = 0;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    sspyr::OctGeom oct[SSPYR_MAX_OCTAVES];
+    size_t frame_floats = 0;                 // floats per output frame slot
+    float* d_out = nullptr;                  // cfg.frames slots
+    unsigned char* d_ext = nullptr;          // extrema flags (optional)
+    size_t ext_frame_bytes = 0;
+    unsigned char* d_in = nullptr;           // cfg.frames input slots
+    size_t in_pitch_bytes = 0, in_frame_bytes = 0, elem_bytes = 4;
+    std::vector<const void*> ext_in;         // per-slot external device input (nullptr = own slot)
+    std::vector<size_t> ext_pitch;
+    std::vector<char> built;
+    float* d_tables = nullptr;
+    std::vector<float> h_tables;
+    std::vector<sspyr::ConvLevel> conv;      // per level
+    float* d_halo = nullptr;                 // CONV row-band halo receive buffers
+    size_t halo_floats = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    int last_launches = 0;
+    sspyr::Tuning tune;
+    std::string err;
+};
+
+namespace sspyr {
+
+// Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
+cudaError_t launch_ref(const sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
+cudaError_t launch_conv(const sspyr_ctx* h, int frame, int* launches);
+cudaError_t launch_conv_step(const sspyr_ctx* h, int frame, int octave, int level, int* launches);
+cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches);
+
+inline const unsigned char* frame_input(const sspyr_ctx* h, int frame, size_t* pitch_bytes) {
+    if (h->ext_in[frame]) {
+        *pitch_bytes = h->ext_pitch[frame];
+        return static_cast<const unsigned char*>(h->ext_in[frame]);
+    }
+    *pitch_bytes = h->in_pitch_bytes;
+    return h->d_in + (size_t)frame * h->in_frame_bytes;
+}
+
+inline float* frame_out(const sspyr_ctx* h, int frame) { return h->d_out + (size_t)frame * h->frame_floats; }
+
+// index of a plane inside an octave block [G_0..G_{S+1} | DoG_0..DoG_{S+1} | G_{S+2}]
+inline int plane_index(int nl, int kind, int level) {
+    if (kind == SSPYR_KIND_GAUSS) return level == nl - 1 ? 2 * nl - 2 : level;
+    if (kind == SSPYR_KIND_DOG) return nl - 1 + level;
+    /* INPLACE */ return nl - 1 + level;   // slots 0..S+1 = DoG, slot S+2 = G_{S+2} (contiguous tail)
+}
+
+}  // namespace sspyr

@@ -1,0 +1,124 @@
+"""CPU suite, part 2: host logic and the C-ABI surface (no compute calls without a GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols() -> list[str]:
+    text = open(os.path.join(ROOT, "include", "sspyr.h")).read()
+    return re.findall(r"^SSPYR_API\s+[\w\s\*]+?\b(sspyr_\w+)\s*\(", text, flags=re.M)
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    declared = _declared_symbols()
+    assert len(declared) >= 25 and len(set(declared)) == len(declared)
+    assert set(declared) == set(pkg._lib.SYMBOLS)                    # the ctypes table tracks the header
+    lib = C.CDLL(pkg._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"libsspyr.so does not export {name}"
+    out = subprocess.run(["nm", "-D", "--defined-only", pkg._lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert {e for e in exported if e.startswith("sspyr_")} == set(declared)
+    assert not [e for e in exported if not e.startswith("sspyr_") and not e.startswith("_")], exported
+
+
+def test_config_struct_matches_the_header(pkg):
+    """sizeof/offsetof as the C compiler sees them == the ctypes mirror."""
+    src = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "sspyr.h"
+    int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(sspyr_config), offsetof(sspyr_config, sigma0),
+        offsetof(sspyr_config, band_row0), offsetof(sspyr_config, extrema_thresh), offsetof(sspyr_config, reserved)); return 0; }
+    '''
+    exe = "/tmp/sspyr_cfg_probe"
+    subprocess.run(["/usr/bin/gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src, text=True, check=True)
+    got = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
+    Cfg = pkg._lib.Config
+    assert got == [C.sizeof(Cfg), Cfg.sigma0.offset, Cfg.band_row0.offset, Cfg.extrema_thresh.offset,
+                   Cfg.reserved.offset]
+
+
+def test_default_config_and_version(pkg):
+    lib = pkg._lib.load()
+    assert lib.sspyr_version() == 100
+    cfg = pkg._lib.Config()
+    assert lib.sspyr_default_config(C.byref(cfg)) == 0
+    assert (cfg.S, cfg.mode, cfg.outputs, cfg.pixel_type, cfg.frames, cfg.device) == (3, 0, 3, 0, 1, -1)
+    assert lib.sspyr_default_config(None) == pkg._lib.ERR_ARG
+
+
+def test_create_rejects_bad_configs_before_touching_cuda(pkg):
+    lib = pkg._lib.load()
+    h = C.c_void_p()
+
+    def rc(**kw):
+        cfg = pkg._lib.Config()
+        lib.sspyr_default_config(C.byref(cfg))
+        cfg.height, cfg.width = 64, 64
+        for k, v in kw.items():
+            setattr(cfg, k, v)
+        return lib.sspyr_create(C.byref(cfg), C.byref(h))
+
+    assert rc(height=0) == pkg._lib.ERR_ARG
+    assert rc(S=-1) == pkg._lib.ERR_ARG
+    assert rc(S=9) == pkg._lib.ERR_UNSUPPORTED            # REF kernels are instantiated for S <= 5
+    assert rc(mode=7) == pkg._lib.ERR_ARG
+    assert rc(octaves=8) == pkg._lib.ERR_ARG              # 64 -> at most 7 octaves (GuassDePyramid.h:48-53)
+    assert rc(full_height=128, band_row0=8, octaves=5) == pkg._lib.ERR_ARG   # band not aligned to 2^(O-1)
+    assert rc(outputs=8) == pkg._lib.ERR_ARG              # EXTREMA without DOG
+    assert b"aligned" in lib.sspyr_last_error(None) or lib.sspyr_last_error(None)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a GPU the product refuses to run (it must never route through the oracle)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.SspyrError) as e:
+        pkg.ScaleSpace(64, 64)
+    assert e.value.code == pkg._lib.ERR_CUDA and "no CPU fallback" in str(e.value)
+    src = "".join(open(os.path.join(ROOT, "sift-parallel-optimization_b200", f)).read()
+                  for f in ("__init__.py", "_lib.py", "pyramid.py", "partition.py", "synth.py"))
+    assert "oracle" not in src.replace("the oracle", "")    # the product package never imports oracle/
+
+
+def test_shard_frames(pkg):
+    for n, world in ((256, 8), (10, 4), (3, 8), (0, 2)):
+        spans = [pkg.shard_frames(n, world, r) for r in range(world)]
+        assert sum(c for _, c in spans) == n
+        pos = 0
+        for first, count in spans:
+            assert first == pos and count in (n // world, n // world + 1)
+            pos += count
+    with pytest.raises(ValueError):
+        pkg.shard_frames(4, 2, 2)
+
+
+@pytest.mark.parametrize("h,octs,world", [(4320, 5, 8), (16384, 8, 8), (1080, 5, 4), (2160, 5, 2), (100, 3, 8),
+                                          (48, 5, 8), (4320, 5, 1)])
+def test_band_rows(pkg, h, octs, world):
+    align = 1 << (octs - 1)
+    spans = [pkg.band_rows(h, octs, world, r) for r in range(world)]
+    pos = 0
+    for row0, rows in spans:
+        if rows == 0:
+            assert row0 == h
+            continue
+        assert row0 == pos and row0 % align == 0                # decimation r<<o stays band-local
+        pos += rows
+        if pos != h:
+            assert rows % align == 0
+        for o in range(octs):                                    # band octave rows tile the full octave rows
+            assert (row0 >> o) + (rows >> o) == (pos >> o)
+    assert pos == h
+    live = [r for _, r in spans if r]
+    assert max(live) - min(live) <= align + h % align
