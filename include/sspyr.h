@@ -151,7 +151,8 @@ SSPYR_API int sspyr_build_stage(sspyr_handle h, int frame, int stage);
 SSPYR_API int sspyr_build_batch(sspyr_handle h, int first, int count);
 SSPYR_API int sspyr_sync(sspyr_handle h);
 /* Device time of the most recent sspyr_build / sspyr_build_batch (CUDA events on the handle's stream);
- * synchronises.  Replaces the wall-clock bracket of main.cpp:67-69. */
+ * synchronises.  Replaces the wall-clock bracket of main.cpp:67-69.  Needs sspyr_set_tuning(h,"timing",1)
+ * first: event records between two builds keep consecutive frames from overlapping, so they are opt-in. */
 SSPYR_API int sspyr_elapsed_ms(sspyr_handle h, float* ms);
 /* Number of kernels the most recent build enqueued. */
 SSPYR_API int sspyr_last_launches(sspyr_handle h);
@@ -168,13 +169,17 @@ SSPYR_API int sspyr_download_gauss(sspyr_handle h, int frame, float* dst);
 /* Device pointer of a plane (valid until sspyr_destroy). */
 SSPYR_API int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind, void** ptr);
 
+/* ---- pinned host memory: lets a C/C++ caller get async copies without including CUDA headers ------- */
+SSPYR_API int sspyr_host_alloc(size_t bytes, void** ptr);
+SSPYR_API int sspyr_host_free(void* ptr);
+
 /* ---- introspection used by the tests ------------------------------------------------------------ */
 /* Copy the window table of (octave, level) out: axis 0 = row window (over this band's rows),
  * axis 1 = column window.  REF mode only (K1, GuassDePyramid.h:118-121). */
 SSPYR_API int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* dst, int capacity);
 /* CONV mode: taps of level s (2R+1 floats, centre at R); returns R through *radius. */
 SSPYR_API int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* radius);
-/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","grid_mult"}; 0 = default. */
+/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing"}; 0 = default. */
 SSPYR_API int sspyr_set_tuning(sspyr_handle h, const char* key, int value);
 
 /* ---- row-band halo exchange (CONV mode, multi-GPU): see DESIGN.md "Row bands" ----------------------- */

@@ -1,14 +1,11 @@
 #!/bin/bash
-# scripts/gpu_round.sh -- what one gpurun call does: GPU tests, smoke, bench, tuning sweep.
+# scripts/gpu_round.sh [sweep workloads...] -- what one gpurun call does: GPU tests, smoke, bench, tuning sweep.
 set -u
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/nvsmi.txt 2>&1
-nproc > gpurun_out/host.txt; grep -m1 "model name" /proc/cpuinfo >> gpurun_out/host.txt
 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-tail -3 gpurun_out/smoke.log
+tail -2 gpurun_out/smoke.log
 python bench.py > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; echo "bench rc=$?"
 cat gpurun_out/bench_c2.json; tail -5 gpurun_out/bench_c2.err
-python bench.py --impl reference > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
-python scripts/sweep_ref.py c2 c3 > gpurun_out/sweep.log 2>&1; grep BEST gpurun_out/sweep.log
+python scripts/sweep_ref.py "${@:-c2 c3}" > gpurun_out/sweep.log 2>&1; grep BEST gpurun_out/sweep.log

@@ -1,5 +1,5 @@
 """scripts/sweep_ref.py -- in-process tuning sweep of the fused REF kernel (one GPU).
-Prints one line per (workload, outputs, rows_per_thread, block, grid_mult): us/frame, GB/s, fraction of peak."""
+Prints one line per (workload, outputs, rows_per_thread, block, bx, pdl): us/frame, GB/s, fraction of peak."""
 from __future__ import annotations
 
 import itertools
@@ -32,8 +32,8 @@ def run(name, outputs, tunings, steps):
         ss.upload(pkg.synth.noise(h, w, frame=s), frame=s)
     ss.sync()
     rows = []
-    for rpt, block, gm in tunings:
-        ss.set_tuning(rows_per_thread=rpt, block=block, grid_mult=gm)
+    for rpt, block, bx, pdl in tunings:
+        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl)
         for i in range(20):
             ss.build(i % slots)
         torch.cuda.synchronize()
@@ -45,19 +45,19 @@ def run(name, outputs, tunings, steps):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / steps * 1e3
         gbs = fb / us / 1e3
-        rows.append((us, rpt, block, gm, gbs))
-        print(f"{name} out={outputs} rpt={rpt} block={block} grid_mult={gm}: {us:8.2f} us/frame  {gbs:7.1f} GB/s  "
+        rows.append((us, rpt, block, bx, pdl, gbs))
+        print(f"{name} out={outputs} rpt={rpt} block={block} bx={bx} pdl={pdl}: {us:8.2f} us/frame  {gbs:7.1f} GB/s  "
               f"frac={gbs / PEAK:.3f}  {h * w / us:9.1f} Mpix/s", flush=True)
     ss.close()
     best = min(rows)
-    print(f"BEST {name} out={outputs}: rpt={best[1]} block={best[2]} grid_mult={best[3]} -> {best[0]:.2f} us, "
-          f"{best[4]:.1f} GB/s, frac={best[4] / PEAK:.3f}", flush=True)
+    print(f"BEST {name} out={outputs}: rpt={best[1]} block={best[2]} bx={best[3]} pdl={best[4]} -> {best[0]:.2f} us, "
+          f"{best[5]:.1f} GB/s, frac={best[5] / PEAK:.3f}", flush=True)
 
 
 if __name__ == "__main__":
     names = sys.argv[1:] or ["c2", "c3"]
-    tunings = list(itertools.product((1, 2, 4, 8), (128, 256), (0, 2, 4, 8)))
+    tunings = list(itertools.product((1, 2, 4), (128, 256), (0, 32), (1, 0)))
     for name in names:
         steps = {"c1": 2000, "c2": 1000, "c3": 300, "c4": 100}[name]
         run(name, pkg.OUT_ALL, tunings, steps)
-    run("c2", pkg.OUT_INPLACE, [(4, 256, 0), (2, 256, 0), (8, 256, 0)], 1000)
+    run("c2", pkg.OUT_INPLACE, [(1, 256, 0, 1), (2, 256, 0, 1), (4, 256, 0, 1), (2, 256, 0, 0)], 1000)

@@ -30,7 +30,7 @@ SYMBOLS = (
     "sspyr_set_stream", "sspyr_upload", "sspyr_set_input_device", "sspyr_build", "sspyr_build_stage",
     "sspyr_build_batch", "sspyr_sync", "sspyr_elapsed_ms", "sspyr_last_launches", "sspyr_download",
     "sspyr_download_inplace", "sspyr_download_gauss", "sspyr_device_ptr", "sspyr_window_table",
-    "sspyr_conv_taps", "sspyr_set_tuning", "sspyr_halo_rows", "sspyr_halo_ptrs", "sspyr_conv_step",
+    "sspyr_host_alloc", "sspyr_host_free", "sspyr_conv_taps", "sspyr_set_tuning", "sspyr_halo_rows", "sspyr_halo_ptrs", "sspyr_conv_step",
 )
 
 
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
         "sspyr_download_inplace": ([H, i, vp], i),
         "sspyr_download_gauss": ([H, i, vp], i),
         "sspyr_device_ptr": ([H, i, i, i, i, C.POINTER(vp)], i),
+        "sspyr_host_alloc": ([sz, C.POINTER(vp)], i),
+        "sspyr_host_free": ([vp], i),
         "sspyr_window_table": ([H, i, i, i, vp, i], i),
         "sspyr_conv_taps": ([H, i, vp, i, pi], i),
         "sspyr_set_tuning": ([H, C.c_char_p, i], i),

@@ -9,8 +9,8 @@
 #define SSPYR_CAT(a, b) SSPYR_CAT2(a, b)
 
 namespace sspyr {
-cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, dim3 grid, int block,
-                                               cudaStream_t st) {
-    return launch_pix<SSPYR_NL>(P, pix, rpt, grid, block, st);
+cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, dim3 grid, dim3 block,
+                                               cudaStream_t st, bool pdl) {
+    return launch_pix<SSPYR_NL>(P, pix, rpt, grid, block, st, pdl);
 }
 }  // namespace sspyr

@@ -16,10 +16,14 @@
 //     quad feeds -- octave 0 always; octave o when r % 2^o == 0 (columns 4j and 4j+2 for o=1, column 4j
 //     for o>=2 when j % 2^(o-2) == 0).  Each input pixel is therefore read from HBM exactly once and no
 //     level is ever materialised before its final value (the reference writes every level 3 times).
+//   * Every load a thread needs (pixel quads of its RPT rows, column windows, row windows) is issued
+//     BEFORE its first store, so a thread pays one DRAM latency, not one per level (stores may alias the
+//     tables as far as the compiler knows, so it cannot hoist them itself).
 //   * 128-bit coalesced loads (ld.global.nc) and streaming stores (st.global.cs): a warp writes 512
-//     contiguous bytes per plane per row; rows are 128-byte aligned (pitch % 32 == 0).
-//   * Column-window values for octave 0 live in registers across the rows a thread walks; row-window
-//     values are warp-uniform broadcast loads.
+//     contiguous bytes per plane per row; rows are 128-byte aligned (pitch % 32 == 0).  Row windows are
+//     stored transposed, [row][8], so one row's S+3 values are two warp-uniform 128-bit loads.
+//   * Launched with programmatic stream serialization and an immediate launch_dependents trigger: the
+//     next frame's grid fills SMs as this one drains (frames are independent), hiding ramp and tail.
 //   * No shared memory, no tensor cores: there is no reuse and 0.3 flop/byte.
 #pragma once
 #include "sspyr_internal.h"
@@ -27,11 +31,6 @@
 namespace sspyr {
 
 namespace {
-
-template <int N> struct Vec;
-template <> struct Vec<1> { using T = float; };
-template <> struct Vec<2> { using T = float2; };
-template <> struct Vec<4> { using T = float4; };
 
 template <int N>
 __device__ __forceinline__ void load_tab(float (&w)[N], const float* __restrict__ p) {
@@ -46,10 +45,26 @@ __device__ __forceinline__ void load_tab(float (&w)[N], const float* __restrict_
     }
 }
 
-// Streaming (evict-first) store of N contiguous floats, the first `nvalid` of which exist.
-template <int N>
+// Row window of one output row: fh_t[row][0..7] (levels padded to 8) -> two uniform 128-bit loads.
+template <int NL>
+__device__ __forceinline__ void load_row_window(float (&f)[NL], const float* __restrict__ fh_t, int orow) {
+    const float4* q = reinterpret_cast<const float4*>(fh_t + (size_t)orow * 8);
+    const float4 a = __ldg(q);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z;
+    if constexpr (NL > 3) f[3] = a.w;
+    if constexpr (NL > 4) {
+        const float4 b = __ldg(q + 1);
+        f[4] = b.x;
+        if constexpr (NL > 5) f[5] = b.y;
+        if constexpr (NL > 6) f[6] = b.z;
+        if constexpr (NL > 7) f[7] = b.w;
+    }
+}
+
+// Streaming (evict-first) store of N contiguous floats; FULL = all N exist (vector store).
+template <int N, bool FULL>
 __device__ __forceinline__ void store_out(float* __restrict__ p, const float (&v)[N], int nvalid) {
-    if (nvalid >= N) {
+    if constexpr (FULL) {
         if constexpr (N == 4) __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
         else if constexpr (N == 2) __stcs(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
         else __stcs(p, v[0]);
@@ -60,14 +75,12 @@ __device__ __forceinline__ void store_out(float* __restrict__ p, const float (&v
     }
 }
 
-// All S+3 levels and S+2 DoGs of N horizontally adjacent pixels of one octave.
-//   w[s][i] : column window of level s at output column ocol+i   (registers)
-template <int NL, int N>
-__device__ __forceinline__ void emit_levels(const RefOct& oc, int outputs, int orow, int ocol,
-                                            const float (&p)[N], const float (&w)[NL][N]) {
-    const int nvalid = oc.W - ocol;
-    float* __restrict__ out = oc.base + (size_t)orow * oc.pitch + ocol;
-    const float* __restrict__ fh = oc.fh + orow;
+// All S+3 levels and S+2 DoGs of N horizontally adjacent pixels of one octave; every operand is already
+// in registers.   out = &plane0[orow][ocol];  planes are `plane` floats apart:
+//   [G_0..G_{S+1} | DoG_0..DoG_{S+1} | G_{S+2}]
+template <int NL, int N, bool FULL>
+__device__ __forceinline__ void emit_levels(float* __restrict__ out, unsigned plane, int outputs, int nvalid,
+                                            const float (&p)[N], const float (&w)[NL][N], const float (&fh)[NL]) {
     const bool want_g = outputs & SSPYR_OUT_GAUSS;
     const bool want_top = outputs & (SSPYR_OUT_GAUSS | SSPYR_OUT_GAUSS_TOP);
     const bool want_d = outputs & SSPYR_OUT_DOG;
@@ -75,21 +88,20 @@ __device__ __forceinline__ void emit_levels(const RefOct& oc, int outputs, int o
     float prev[N];
 #pragma unroll
     for (int s = 0; s < NL; ++s) {
-        const float f = __ldg(fh + (size_t)s * oc.H);
         float g[N];
 #pragma unroll
         for (int i = 0; i < N; ++i)
-            g[i] = init_only ? p[i] : __fmul_rn(__fmul_rn(p[i], w[s][i]), f);         // K2 then K3
+            g[i] = init_only ? p[i] : __fmul_rn(__fmul_rn(p[i], w[s][i]), fh[s]);      // K2 then K3
         if (s < NL - 1) {
-            if (want_g) store_out<N>(out + (size_t)s * oc.plane, g, nvalid);
+            if (want_g) store_out<N, FULL>(out + (size_t)s * plane, g, nvalid);
         } else {
-            if (want_top) store_out<N>(out + (size_t)(2 * NL - 2) * oc.plane, g, nvalid);
+            if (want_top) store_out<N, FULL>(out + (size_t)(2 * NL - 2) * plane, g, nvalid);
         }
         if (s > 0 && want_d) {
             float d[N];
 #pragma unroll
             for (int i = 0; i < N; ++i) d[i] = __fsub_rn(prev[i], g[i]);               // K4
-            store_out<N>(out + (size_t)(NL - 1 + s - 1) * oc.plane, d, nvalid);
+            store_out<N, FULL>(out + (size_t)(NL - 1 + s - 1) * plane, d, nvalid);
         }
 #pragma unroll
         for (int i = 0; i < N; ++i) prev[i] = g[i];
@@ -97,9 +109,16 @@ __device__ __forceinline__ void emit_levels(const RefOct& oc, int outputs, int o
 }
 
 template <int NL, int N>
-__device__ __forceinline__ void load_windows(float (&w)[NL][N], const RefOct& oc, int ocol) {
+__device__ __forceinline__ void load_windows(float (&w)[NL][N], const float* __restrict__ fw, int pitch, int ocol) {
 #pragma unroll
-    for (int s = 0; s < NL; ++s) load_tab<N>(w[s], oc.fw + (size_t)s * oc.pitch + ocol);
+    for (int s = 0; s < NL; ++s) load_tab<N>(w[s], fw + (size_t)s * pitch + ocol);
+}
+
+template <int NL, int N>
+__device__ __forceinline__ void emit_dispatch(float* __restrict__ out, unsigned plane, int outputs, int nvalid,
+                                              const float (&p)[N], const float (&w)[NL][N], const float (&fh)[NL]) {
+    if (nvalid >= N) emit_levels<NL, N, true>(out, plane, outputs, nvalid, p, w, fh);
+    else emit_levels<NL, N, false>(out, plane, outputs, nvalid, p, w, fh);
 }
 
 // One input quad -> float pixels (K0's int->float cast, GuassDePyramid.h:80).
@@ -108,15 +127,15 @@ __device__ __forceinline__ void load_quad(float (&p)[4], const unsigned char* __
     if (c + 4 <= W) {
         if constexpr (PIX == SSPYR_PIXEL_I32) {
             int4 v;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                         : "l"(reinterpret_cast<const int4*>(row) + (c >> 2)));
+            asm("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                : "l"(reinterpret_cast<const int4*>(row) + (c >> 2)));
             p[0] = (float)v.x; p[1] = (float)v.y; p[2] = (float)v.z; p[3] = (float)v.w;
         } else if constexpr (PIX == SSPYR_PIXEL_F32) {
             float4 v;
-            asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                         : "l"(reinterpret_cast<const float4*>(row) + (c >> 2)));
+            asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                : "l"(reinterpret_cast<const float4*>(row) + (c >> 2)));
             p[0] = v.x; p[1] = v.y; p[2] = v.z; p[3] = v.w;
         } else {
             const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(row) + (c >> 2));
@@ -138,85 +157,128 @@ __device__ __forceinline__ void load_quad(float (&p)[4], const unsigned char* __
 
 template <int PIX> __host__ __device__ constexpr int elem_bytes() { return PIX == SSPYR_PIXEL_U8 ? 1 : 4; }
 
-// grid.x : chunks of (row group, quad) work items, quads fastest;  grid.y : frame within the batch.
+// grid.x: blocks of BX quads along a row;  grid.y: blocks of BY row groups (RPT rows each);  grid.z: frame.
 template <int NL, int PIX, int RPT>
 __global__ void __launch_bounds__(256)
 ref_fused_kernel(const __grid_constant__ RefParams P) {
-    const int W4 = (P.W + 3) >> 2;
-    const int groups = (P.H + RPT - 1) / RPT;
-    const long long items = (long long)W4 * groups;
+    // Frames are independent: let the next launch in the stream start filling SMs right away (PDL).
+    asm volatile("griddepcontrol.launch_dependents;");
+
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;            // quad index along the row
+    const int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * RPT;   // first of this thread's RPT rows
+    const int c = j << 2;
+    if (c >= P.W || r0 >= P.H) return;
     const unsigned char* __restrict__ img =
-        static_cast<const unsigned char*>(P.img) + (size_t)blockIdx.y * P.img_frame_stride;
-    const size_t fofs = (size_t)blockIdx.y * P.out_frame_stride;
+        static_cast<const unsigned char*>(P.img) + (size_t)blockIdx.z * P.img_frame_stride;
+    const size_t fofs = (size_t)blockIdx.z * P.out_frame_stride;
+    const int outputs = P.outputs;
 
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < items;
-         t += (long long)gridDim.x * blockDim.x) {
-        const int j = (int)(t % W4);
-        const int rg = (int)(t / W4);
-        const int c = j << 2;
-
-        RefOct o0 = P.oct[0];
-        o0.base += fofs;
-        float w0[NL][4];
-        load_windows<NL, 4>(w0, o0, c);
-
-        const int r_end = min(P.H, (rg + 1) * RPT);
+    // ---- issue every load first -------------------------------------------------------------------
+    float p[RPT][4];
 #pragma unroll
-        for (int rr = 0; rr < RPT; ++rr) {
-            const int r = rg * RPT + rr;
-            if (r >= r_end) break;
-            float p[4];
-            load_quad<PIX>(p, img + (size_t)r * P.img_pitch * elem_bytes<PIX>(), c, P.W);
-            emit_levels<NL, 4>(o0, P.outputs, r, c, p, w0);
+    for (int rr = 0; rr < RPT; ++rr) {
+        const int r = min(r0 + rr, P.H - 1);                        // clamp: rows past the end are not stored
+        load_quad<PIX>(p[rr], img + (size_t)r * P.img_pitch * elem_bytes<PIX>(), c, P.W);
+    }
+    const RefOct& o0 = P.oct[0];
+    float w0[NL][4];
+    load_windows<NL, 4>(w0, o0.fw, o0.pitch, c);
+    float f0[RPT][NL];
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) load_row_window<NL>(f0[rr], o0.fh, min(r0 + rr, P.H - 1));
 
-            // higher octaves fed by this quad: r % 2^o == 0 and the column phase matches
-            if ((r & 1) == 0 && P.octaves > 1) {
-                {   // octave 1: input columns c, c+2 -> output columns c/2, c/2+1
-                    RefOct o1 = P.oct[1];
-                    const int orow = r >> 1, ocol = c >> 1;
-                    if (orow < o1.H && ocol < o1.W) {
-                        o1.base += fofs;
-                        const float p2[2] = {p[0], p[2]};
-                        float w1[NL][2];
-                        load_windows<NL, 2>(w1, o1, ocol);
-                        emit_levels<NL, 2>(o1, P.outputs, orow, ocol, p2, w1);
-                    }
-                }
-                for (int o = 2; o < P.octaves; ++o) {
-                    if ((r & ((1 << o) - 1)) != 0) break;
-                    if ((j & ((1 << (o - 2)) - 1)) != 0) break;   // column 4j must be a multiple of 2^o
-                    RefOct oc = P.oct[o];
-                    const int orow = r >> o, ocol = c >> o;
-                    if (orow < oc.H && ocol < oc.W) {
-                        oc.base += fofs;
-                        const float p1[1] = {p[0]};
-                        float w1[NL][1];
-                        load_windows<NL, 1>(w1, oc, ocol);
-                        emit_levels<NL, 1>(oc, P.outputs, orow, ocol, p1, w1);
-                    }
-                }
+    // octave 1 is fed by the even rows of this thread (r0 is a multiple of RPT): input columns c, c+2
+    constexpr int R1 = (RPT + 1) / 2;
+    const bool even0 = (RPT > 1) || ((r0 & 1) == 0);
+    const RefOct& o1 = P.oct[1];
+    const int ocol1 = c >> 1;
+    const bool has1 = P.octaves > 1 && even0 && ocol1 < o1.W;
+    float w1[NL][2];
+    float f1[R1][NL];
+    if (has1) {
+        load_windows<NL, 2>(w1, o1.fw, o1.pitch, ocol1);
+#pragma unroll
+        for (int k = 0; k < R1; ++k) load_row_window<NL>(f1[k], o1.fh, min((r0 >> 1) + k, o1.H - 1));
+    }
+
+    // ---- octave 0 -----------------------------------------------------------------------------------
+    float* out0 = o0.base + fofs + (size_t)r0 * o0.pitch + c;
+    const int nvalid0 = o0.W - c;
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr)
+        if (r0 + rr < P.H)
+            emit_dispatch<NL, 4>(out0 + (size_t)rr * o0.pitch, (unsigned)o0.plane, outputs, nvalid0, p[rr], w0, f0[rr]);
+
+    // ---- octave 1 -----------------------------------------------------------------------------------
+    if (has1) {
+        float* out1 = o1.base + fofs + (size_t)(r0 >> 1) * o1.pitch + ocol1;
+        const int nvalid1 = o1.W - ocol1;
+#pragma unroll
+        for (int k = 0; k < R1; ++k) {
+            const int orow = (r0 >> 1) + k;
+            if (orow < o1.H && r0 + 2 * k < P.H) {
+                const float p2[2] = {p[2 * k < RPT ? 2 * k : 0][0], p[2 * k < RPT ? 2 * k : 0][2]};
+                emit_dispatch<NL, 2>(out1 + (size_t)k * o1.pitch, (unsigned)o1.plane, outputs, nvalid1, p2, w1, f1[k]);
             }
         }
     }
+
+    // ---- octaves >= 2: one pixel per participating quad (1/16 of the octave-0 work and falling) -------
+#pragma unroll
+    for (int rr = 0; rr < RPT; rr += 4) {
+        const int r = r0 + rr;
+        if (r >= P.H) break;
+        for (int o = 2; o < P.octaves; ++o) {
+            if ((r & ((1 << o) - 1)) != 0) break;
+            if ((j & ((1 << (o - 2)) - 1)) != 0) break;             // column 4j must be a multiple of 2^o
+            const RefOct& oc = P.oct[o];
+            const int orow = r >> o, ocol = c >> o;
+            if (orow < oc.H && ocol < oc.W) {
+                const float p1[1] = {p[rr][0]};
+                float wv[NL][1];
+                float fv[NL];
+                load_windows<NL, 1>(wv, oc.fw, oc.pitch, ocol);
+                load_row_window<NL>(fv, oc.fh, orow);
+                emit_levels<NL, 1, true>(oc.base + fofs + (size_t)orow * oc.pitch + ocol, (unsigned)oc.plane, outputs,
+                                         1, p1, wv, fv);
+            }
+        }
+    }
+    // Chain completion: this grid may not finish before the grid it overlapped with has finished and
+    // flushed, so "kernel N+1 done" always implies "kernel N done" for whatever follows in the stream.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <int NL, int PIX, int RPT>
+cudaError_t launch_one(const RefParams& P, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ref_fused_kernel<NL, PIX, RPT>, P);
 }
 
 template <int NL, int PIX>
-cudaError_t launch_rpt(const RefParams& P, int rpt, dim3 grid, int block, cudaStream_t st) {
+cudaError_t launch_rpt(const RefParams& P, int rpt, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     switch (rpt) {
-        case 1: ref_fused_kernel<NL, PIX, 1><<<grid, block, 0, st>>>(P); break;
-        case 2: ref_fused_kernel<NL, PIX, 2><<<grid, block, 0, st>>>(P); break;
-        case 4: ref_fused_kernel<NL, PIX, 4><<<grid, block, 0, st>>>(P); break;
-        default: ref_fused_kernel<NL, PIX, 8><<<grid, block, 0, st>>>(P); break;
+        case 1: return launch_one<NL, PIX, 1>(P, grid, block, st, pdl);
+        case 2: return launch_one<NL, PIX, 2>(P, grid, block, st, pdl);
+        default: return launch_one<NL, PIX, 4>(P, grid, block, st, pdl);
     }
-    return cudaGetLastError();
 }
 
 template <int NL>
-cudaError_t launch_pix(const RefParams& P, int pix, int rpt, dim3 grid, int block, cudaStream_t st) {
+cudaError_t launch_pix(const RefParams& P, int pix, int rpt, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     switch (pix) {
-        case SSPYR_PIXEL_I32: return launch_rpt<NL, SSPYR_PIXEL_I32>(P, rpt, grid, block, st);
-        case SSPYR_PIXEL_F32: return launch_rpt<NL, SSPYR_PIXEL_F32>(P, rpt, grid, block, st);
-        default: return launch_rpt<NL, SSPYR_PIXEL_U8>(P, rpt, grid, block, st);
+        case SSPYR_PIXEL_I32: return launch_rpt<NL, SSPYR_PIXEL_I32>(P, rpt, grid, block, st, pdl);
+        case SSPYR_PIXEL_F32: return launch_rpt<NL, SSPYR_PIXEL_F32>(P, rpt, grid, block, st, pdl);
+        default: return launch_rpt<NL, SSPYR_PIXEL_U8>(P, rpt, grid, block, st, pdl);
     }
 }
 

@@ -4,7 +4,7 @@
 
 namespace sspyr {
 
-#define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, dim3, int, cudaStream_t);
+#define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, dim3, dim3, cudaStream_t, bool);
 SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 #undef SSPYR_DECL
 
@@ -54,28 +54,35 @@ cudaError_t launch_ref(const sspyr_ctx* h, int first, int count, int outputs, in
         }
 
         int rpt = h->tune.rows_per_thread;
-        if (rpt <= 0) rpt = 4;
-        rpt = rpt >= 8 ? 8 : rpt >= 4 ? 4 : rpt >= 2 ? 2 : 1;
-        int block = h->tune.block > 0 ? h->tune.block : 256;
-        block = block > 256 ? 256 : (block < 32 ? 32 : (block / 32) * 32);
-        const long long items = (long long)((P.W + 3) >> 2) * ((P.H + rpt - 1) / rpt);
-        long long gx = (items + block - 1) / block;
-        if (h->tune.grid_mult > 0) {
-            const long long cap = (long long)sm_count(h->device) * h->tune.grid_mult;
-            if (gx > cap) gx = cap;
+        if (rpt <= 0) rpt = 2;
+        rpt = rpt >= 4 ? 4 : rpt >= 2 ? 2 : 1;
+        int threads = h->tune.block > 0 ? h->tune.block : 256;
+        threads = threads > 256 ? 256 : (threads < 32 ? 32 : (threads / 32) * 32);
+        const int W4 = (P.W + 3) >> 2;
+        int bx = h->tune.bx;
+        if (bx <= 0) {   // widest CTA row among {128,96,64,32} that wastes the fewest padded quads
+            int best_waste = 1 << 30;
+            for (int cand : {128, 96, 64, 32}) {
+                if (cand > threads) continue;
+                const int waste = (W4 + cand - 1) / cand * cand - W4;
+                if (waste < best_waste) { best_waste = waste; bx = cand; }
+            }
         }
-        if (gx < 1) gx = 1;
-        if (gx > 0x7fffffffLL) gx = 0x7fffffffLL;
-        const dim3 grid((unsigned)gx, (unsigned)n, 1);
+        bx = bx > threads ? threads : (bx < 32 ? 32 : (bx / 32) * 32);
+        const int by = threads / bx > 0 ? threads / bx : 1;
+        const int row_groups = (P.H + rpt - 1) / rpt;
+        const dim3 block(bx, by, 1);
+        const dim3 grid((W4 + bx - 1) / bx, (row_groups + by - 1) / by, n);
+        const bool pdl = h->tune.pdl != 0;
 
         cudaError_t e;
         switch (h->nl) {
-            case 3: e = launch_ref_nl3(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
-            case 4: e = launch_ref_nl4(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
-            case 5: e = launch_ref_nl5(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
-            case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
-            case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
-            case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, grid, block, h->stream); break;
+            case 3: e = launch_ref_nl3(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 4: e = launch_ref_nl4(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 5: e = launch_ref_nl5(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
             default: return cudaErrorInvalidValue;   // S in 0..5 (create() rejects the rest for REF mode)
         }
         if (e != cudaSuccess) return e;

@@ -194,6 +194,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
         }
         g.pitch = (int)round_up((size_t)g.W, 32);
         g.plane = (size_t)g.H * g.pitch;
+        if (g.plane >= (1ull << 32)) return bail(SSPYR_ERR_UNSUPPORTED, "a level plane exceeds 2^32 floats");
         g.off = off;
         off += (size_t)(2 * nl - 1) * g.plane;
         g.ext_off = ext;
@@ -202,7 +203,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             g.fw_off = tab;
             tab += (size_t)nl * g.pitch;
             g.fh_off = tab;
-            tab += round_up((size_t)nl * g.H, 32);
+            tab += (size_t)8 * g.H;                       // transposed [H][8]
         }
     }
     h->frame_floats = round_up(off, 64);
@@ -219,7 +220,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
                 ref_window(cfg.width, o, s, cfg.sigma0, full.data());
                 std::memcpy(&h->h_tables[g.fw_off + (size_t)s * g.pitch], full.data(), sizeof(float) * g.W);
                 ref_window(cfg.full_height, o, s, cfg.sigma0, full.data());
-                std::memcpy(&h->h_tables[g.fh_off + (size_t)s * g.H], full.data() + r0, sizeof(float) * g.H);
+                for (int r = 0; r < g.H; ++r) h->h_tables[g.fh_off + (size_t)r * 8 + s] = full[r0 + r];
             }
         }
     } else {
@@ -346,7 +347,7 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
     if (!valid_frame(h, first) || count < 1) return fail(h, SSPYR_ERR_ARG, "bad frame range");
     CU(h, cudaSetDevice(h->device));
     int launches = 0;
-    CU(h, cudaEventRecord(h->ev0, h->stream));
+    if (h->tune.timing) CU(h, cudaEventRecord(h->ev0, h->stream));
     cudaError_t e = cudaSuccess;
     if (h->cfg.mode == SSPYR_MODE_REF) {
         e = launch_ref(h, first, count, h->cfg.outputs, &launches);
@@ -360,8 +361,8 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
         }
     }
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
-    CU(h, cudaEventRecord(h->ev1, h->stream));
-    h->timed = true;
+    if (h->tune.timing) CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = h->tune.timing != 0;
     h->last_launches = launches;
     for (int i = 0; i < count; ++i) h->built[(first + i) % h->cfg.frames] = 1;
     return SSPYR_OK;
@@ -378,12 +379,12 @@ int sspyr_build_stage(sspyr_handle h, int frame, int stage) {
     if (!(h->cfg.outputs & SSPYR_OUT_GAUSS)) return fail(h, SSPYR_ERR_STATE, "partial stages need SSPYR_OUT_GAUSS");
     CU(h, cudaSetDevice(h->device));
     int launches = 0;
-    CU(h, cudaEventRecord(h->ev0, h->stream));
+    if (h->tune.timing) CU(h, cudaEventRecord(h->ev0, h->stream));
     const int outputs = SSPYR_OUT_GAUSS | (stage == SSPYR_STAGE_INIT ? SSPYR_INT_INIT_ONLY : 0);
     const cudaError_t e = launch_ref(h, frame, 1, outputs, &launches);
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
-    CU(h, cudaEventRecord(h->ev1, h->stream));
-    h->timed = true;
+    if (h->tune.timing) CU(h, cudaEventRecord(h->ev1, h->stream));
+    h->timed = h->tune.timing != 0;
     h->last_launches = launches;
     h->built[frame] = 1;
     return SSPYR_OK;
@@ -398,7 +399,7 @@ int sspyr_sync(sspyr_handle h) {
 
 int sspyr_elapsed_ms(sspyr_handle h, float* ms) {
     if (!h || !ms) return SSPYR_ERR_ARG;
-    if (!h->timed) return fail(h, SSPYR_ERR_STATE, "no build has been enqueued yet");
+    if (!h->timed) return fail(h, SSPYR_ERR_STATE, "no timed build yet (enable with sspyr_set_tuning(h, \"timing\", 1))");
     CU(h, cudaEventSynchronize(h->ev1));
     CU(h, cudaEventElapsedTime(ms, h->ev0, h->ev1));
     return SSPYR_OK;
@@ -480,6 +481,28 @@ int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
     return SSPYR_OK;
 }
 
+int sspyr_host_alloc(size_t bytes, void** ptr) {
+    if (!ptr) return SSPYR_ERR_ARG;
+    *ptr = nullptr;
+    const cudaError_t e = cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? SSPYR_ERR_NOMEM : SSPYR_ERR_CUDA,
+                    std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    }
+    return SSPYR_OK;
+}
+
+int sspyr_host_free(void* ptr) {
+    if (!ptr) return SSPYR_OK;
+    const cudaError_t e = cudaFreeHost(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, SSPYR_ERR_CUDA, std::string("cudaFreeHost: ") + cudaGetErrorString(e));
+    }
+    return SSPYR_OK;
+}
+
 int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* dst, int capacity) {
     if (!h || !dst) return SSPYR_ERR_ARG;
     if (h->cfg.mode != SSPYR_MODE_REF) return fail(h, SSPYR_ERR_STATE, "window tables exist in REF mode only");
@@ -488,10 +511,14 @@ int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* d
     const OctGeom& g = h->oct[octave];
     const int n = axis == 0 ? g.H : g.W;
     if (capacity < n) return fail(h, SSPYR_ERR_ARG, "destination too small");
-    const size_t off = axis == 0 ? g.fh_off + (size_t)level * g.H : g.fw_off + (size_t)level * g.pitch;
     // read back from the DEVICE copy: this is what the kernel actually multiplies by
     CU(h, cudaSetDevice(h->device));
-    CU(h, cudaMemcpy(dst, h->d_tables + off, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    if (axis == 1) {
+        CU(h, cudaMemcpy(dst, h->d_tables + g.fw_off + (size_t)level * g.pitch, sizeof(float) * n, cudaMemcpyDeviceToHost));
+    } else {   // row window is stored transposed, [row][8]
+        CU(h, cudaMemcpy2D(dst, sizeof(float), h->d_tables + g.fh_off + level, 8 * sizeof(float), sizeof(float), n,
+                           cudaMemcpyDeviceToHost));
+    }
     return n;
 }
 
@@ -511,7 +538,9 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     if (!h || !key) return SSPYR_ERR_ARG;
     if (!std::strcmp(key, "rows_per_thread")) h->tune.rows_per_thread = value;
     else if (!std::strcmp(key, "block")) h->tune.block = value;
-    else if (!std::strcmp(key, "grid_mult")) h->tune.grid_mult = value;
+    else if (!std::strcmp(key, "bx")) h->tune.bx = value;
+    else if (!std::strcmp(key, "pdl")) h->tune.pdl = value;
+    else if (!std::strcmp(key, "timing")) h->tune.timing = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
     return SSPYR_OK;
 }

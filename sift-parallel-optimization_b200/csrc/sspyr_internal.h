@@ -21,7 +21,7 @@ struct OctGeom {
     size_t plane = 0;          // H * pitch floats
     size_t off = 0;            // float offset of this octave inside a frame slot
     size_t fw_off = 0;         // REF: float offset of the column-window table [NL][pitch] in d_tables
-    size_t fh_off = 0;         // REF: float offset of the row-window table    [NL][H]
+    size_t fh_off = 0;         // REF: float offset of the row-window table    [H][8] (transposed)
     size_t ext_off = 0;        // byte offset of the extrema planes [S][H][pitch] inside an extrema slot
 };
 
@@ -29,7 +29,7 @@ struct OctGeom {
 struct RefOct {
     float* base;               // [G_0..G_{S+1} | DoG_0..DoG_{S+1} | G_{S+2}] of frame 0 of the launch
     const float* fw;           // [NL][pitch]
-    const float* fh;           // [NL][H]
+    const float* fh;           // [H][8]: row window, transposed (levels padded to 8)
     int H, W, pitch;
     unsigned long long plane;
 };
@@ -46,9 +46,12 @@ struct RefParams {
 };
 
 struct Tuning {
-    int rows_per_thread = 0;   // 0 = heuristic
-    int block = 0;
-    int grid_mult = 0;         // CTAs per SM for the grid-stride launch; 0 = one CTA per work chunk
+    int rows_per_thread = 0;   // 0 = default
+    int block = 0;             // threads per CTA
+    int bx = 0;                // CTA width in quads (threads along a row); 0 = pick the least-padding width
+    int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
+    int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
+                               // launches stop them from overlapping, so this is off unless asked for
 };
 
 // CONV mode: one level step (see conv_kernels.cu)

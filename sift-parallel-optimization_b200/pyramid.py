@@ -209,6 +209,7 @@ class GaussPyramid:
         self.S = int(S)
         self.data = np.array(img[:len, :len], dtype=np.int32, order="C")          # deep copy, :38-46
         self._ss = ScaleSpace(self.length, self.length, 0, self.S, outputs=L.OUT_ALL, device=device)
+        self._ss.set_tuning(timing=1)
         self.layer = self._ss.octaves                                              # :48-53
         self._ss.upload(self.data)
         self.GaussPyInit()                                                         # :57

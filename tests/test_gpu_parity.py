@@ -169,6 +169,9 @@ def test_frame_slots_batch_and_rebuild(pkg, O, synth):
     h, w, n = 72, 100, 5
     frames = [synth.noise(h, w, frame=f) for f in range(n)]
     with pkg.ScaleSpace(h, w, 3, 3, frames=n) as ss:
+        with pytest.raises(pkg.SspyrError):
+            ss.elapsed_ms()                                                  # timing is opt-in
+        ss.set_tuning(timing=1)
         for f in range(n):
             ss.upload(frames[f], frame=f)
         ss.build_batch(0, n)
@@ -205,13 +208,14 @@ def test_device_resident_input_via_torch(pkg, O, synth):
             ss.set_input_device(t.data_ptr() + 4, 0)                         # misaligned
 
 
-@pytest.mark.parametrize("rpt,block,grid_mult", [(1, 128, 0), (2, 256, 0), (8, 64, 0), (4, 256, 2), (8, 256, 1)])
-def test_every_tuning_is_bit_exact(pkg, O, synth, rpt, block, grid_mult):
+@pytest.mark.parametrize("rpt,block,bx,pdl", [(1, 128, 0, 1), (2, 256, 32, 1), (4, 64, 64, 0), (4, 256, 128, 1),
+                                              (1, 256, 96, 0), (2, 96, 96, 1)])
+def test_every_tuning_is_bit_exact(pkg, O, synth, rpt, block, bx, pdl):
     h, w = 203, 330
     img = synth.noise(h, w)
     ref = O.ref_build(img, octaves=5, S=3)
     with pkg.ScaleSpace(h, w, 5, 3) as ss:
-        ss.set_tuning(rows_per_thread=rpt, block=block, grid_mult=grid_mult)
+        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl)
         ss.upload(img)
         ss.build()
         for o, a in enumerate(ss.download_gauss()):
