@@ -23,7 +23,7 @@ int sm_count(int device) {
 
 // Enqueue the fused REF build of frame slots first .. first+count-1 (one launch when the slots are the
 // handle's own contiguous buffers; one launch per frame when a slot reads an external device image).
-cudaError_t launch_ref(const sspyr_ctx* h, int first, int count, int outputs, int* launches) {
+cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* launches) {
     const int frames = h->cfg.frames;
     int done = 0;
     while (done < count) {
@@ -54,9 +54,9 @@ cudaError_t launch_ref(const sspyr_ctx* h, int first, int count, int outputs, in
         }
 
         int rpt = h->tune.rows_per_thread;
-        if (rpt <= 0) rpt = 2;
+        if (rpt <= 0) rpt = 2;                       // measured best on C2..C4 (profiles/, sweep_ref.py)
         rpt = rpt >= 4 ? 4 : rpt >= 2 ? 2 : 1;
-        int threads = h->tune.block > 0 ? h->tune.block : 256;
+        int threads = h->tune.block > 0 ? h->tune.block : 128;
         threads = threads > 256 ? 256 : (threads < 32 ? 32 : (threads / 32) * 32);
         const int W4 = (P.W + 3) >> 2;
         int bx = h->tune.bx;
@@ -73,7 +73,15 @@ cudaError_t launch_ref(const sspyr_ctx* h, int first, int count, int outputs, in
         const int row_groups = (P.H + rpt - 1) / rpt;
         const dim3 block(bx, by, 1);
         const dim3 grid((W4 + bx - 1) / bx, (row_groups + by - 1) / by, n);
-        const bool pdl = h->tune.pdl != 0;
+        // Overlap with the previous launch only when it wrote other frame slots: two builds of the SAME slot
+        // (e.g. a K0-only stage followed by the full build) must stay ordered or their stores would race.
+        bool clash = false;
+        for (int k = 0; k < n; ++k)
+            for (int q = 0; q < h->last_count; ++q)
+                clash |= ((f0 + k) % frames) == ((h->last_first + q) % frames);
+        const bool pdl = h->tune.pdl != 0 && !clash;
+        h->last_first = f0;
+        h->last_count = n;
 
         cudaError_t e;
         switch (h->nl) {

@@ -86,6 +86,7 @@ struct sspyr_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int last_launches = 0;
+    int last_first = 0, last_count = 0;      // frame slots the previous kernel wrote (PDL overlap guard)
     sspyr::Tuning tune;
     std::string err;
 };
@@ -93,7 +94,7 @@ struct sspyr_ctx {
 namespace sspyr {
 
 // Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
-cudaError_t launch_ref(const sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
+cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
 cudaError_t launch_conv(const sspyr_ctx* h, int frame, int* launches);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int frame, int octave, int level, int* launches);
 cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches);
