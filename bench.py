@@ -86,8 +86,21 @@ class Dist:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", "29511")
             kw = {"device_id": self.dev} if backend == "nccl" else {}
-            dist.init_process_group(backend=backend, **kw)
-            self.dist = dist
+            # NCCL announces its version on fd 1 during the first collective; stdout must carry ONE JSON line,
+            # so point fd 1 at stderr until the communicator exists.
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group(backend=backend, **kw)
+                self.dist = dist
+                dist.barrier()
+                if backend == "nccl":
+                    torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier(self):
         if self.world > 1:

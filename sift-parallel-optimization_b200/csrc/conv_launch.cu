@@ -1,0 +1,120 @@
+// csrc/conv_launch.cu -- host side of CONV mode: per-level launches of conv_kernel.cuh, the decimation chain
+// between octaves, row-band halo staging, and the DoG extremum scan.  Also the halo part of the C ABI.
+#include <cstring>
+
+#include "conv_kernel.cuh"
+
+namespace sspyr {
+
+#define SSPYR_DECL(n) cudaError_t launch_conv_r##n(const ConvParams&, int, dim3, cudaStream_t, int);
+SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
+SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_DECL(14) SSPYR_DECL(15) SSPYR_DECL(16)
+SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
+#undef SSPYR_DECL
+cudaError_t launch_extrema_octave(const float*, unsigned char*, int, int, int, int, unsigned long long, float, cudaStream_t);
+
+namespace {
+
+// compiled radius that serves a requested one (taps are zero-padded up to it)
+int compiled_radius(int r) { return r <= 16 ? r : r <= 20 ? 20 : r <= 24 ? 24 : r <= 28 ? 28 : 32; }
+
+cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, dim3 grid, cudaStream_t st, int device) {
+    switch (rt) {
+#define SSPYR_CASE(n) case n: return launch_conv_r##n(P, src_kind, grid, st, device);
+        SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
+        SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12) SSPYR_CASE(13) SSPYR_CASE(14) SSPYR_CASE(15)
+        SSPYR_CASE(16) SSPYR_CASE(20) SSPYR_CASE(24) SSPYR_CASE(28) SSPYR_CASE(32)
+#undef SSPYR_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+bool conv_has_up(const sspyr_ctx* h) { return h->cfg.band_row0 > 0; }
+bool conv_has_down(const sspyr_ctx* h) { return h->cfg.band_row0 + h->cfg.height < h->cfg.full_height; }
+
+float* conv_halo_plane(const sspyr_ctx* h, int octave, int down) {
+    return h->d_halo + h->halo_off[octave] + (size_t)down * h->halo_rmax * h->oct[octave].pitch;
+}
+
+unsigned char* conv_halo_raw(const sspyr_ctx* h, int down) {
+    return h->d_halo_raw + (size_t)down * h->halo_rmax * h->in_pitch_bytes;
+}
+
+// The blur that PRODUCES (octave, level) for frame slots first..first+count-1 (contiguous, own input slots).
+cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octave, int level, int* launches) {
+    if (level == 0 && octave > 0) return cudaSuccess;      // written by the decimating epilogue of (octave-1, S)
+    const int nl = h->nl, S = h->cfg.S;
+    const OctGeom& g = h->oct[octave];
+    ConvParams P{};
+    int src_kind;
+    if (level == 0) {                                        // octave 0 from the raw frame
+        size_t pitch_bytes = 0;
+        P.src = frame_input(h, first, &pitch_bytes);
+        P.src_pitch = (int)(pitch_bytes / h->elem_bytes);
+        P.src_frame_stride = h->in_frame_bytes / h->elem_bytes;
+        src_kind = h->cfg.pixel_type;
+        P.top_halo = conv_has_up(h) ? conv_halo_raw(h, 0) : nullptr;
+        P.bot_halo = conv_has_down(h) ? conv_halo_raw(h, 1) : nullptr;
+    } else {
+        P.src = frame_out(h, first) + g.off + (size_t)plane_index(nl, SSPYR_KIND_GAUSS, level - 1) * g.plane;
+        P.src_pitch = g.pitch;
+        P.src_frame_stride = h->frame_floats;
+        src_kind = CONV_SRC_PLANE;
+        P.top_halo = conv_has_up(h) ? conv_halo_plane(h, octave, 0) : nullptr;
+        P.bot_halo = conv_has_down(h) ? conv_halo_plane(h, octave, 1) : nullptr;
+    }
+    const int R = h->conv[level].radius;
+    const int RT = compiled_radius(R);
+    P.halo_rows = R;
+    float* obase = frame_out(h, first) + g.off;
+    P.dst_g = obase + (size_t)plane_index(nl, SSPYR_KIND_GAUSS, level) * g.plane;
+    P.dst_d = (level >= 1 && (h->cfg.outputs & SSPYR_OUT_DOG))
+                  ? obase + (size_t)plane_index(nl, SSPYR_KIND_DOG, level - 1) * g.plane : nullptr;
+    P.dst_frame_stride = h->frame_floats;
+    P.dst_pitch = g.pitch;
+    P.H = g.H;
+    P.W = g.W;
+    if (level == S && octave + 1 < h->octaves) {
+        const OctGeom& n = h->oct[octave + 1];
+        P.dst_dec = frame_out(h, first) + n.off;             // G_0 of the next octave
+        P.dec_pitch = n.pitch;
+        P.dec_H = n.H;
+        P.dec_W = n.W;
+    }
+    std::memset(P.taps, 0, sizeof(P.taps));
+    std::memcpy(P.taps + (RT - R), h->h_tables.data() + h->conv[level].taps_off, sizeof(float) * (2 * R + 1));
+    const int TH = RT <= 10 ? 64 : 32;
+    const dim3 grid((g.W + CONV_TW - 1) / CONV_TW, (g.H + TH - 1) / TH, count);
+    const cudaError_t e = dispatch(RT, P, src_kind, grid, h->stream, h->device);
+    if (e == cudaSuccess) ++*launches;
+    return e;
+}
+
+// Whole pyramid of one or more frame slots (no row bands: a banded handle is driven level by level so that the
+// host can exchange halos between steps).
+cudaError_t launch_conv(const sspyr_ctx* h, int first, int count, int* launches) {
+    for (int o = 0; o < h->octaves; ++o)
+        for (int s = 0; s < h->nl; ++s) {
+            const cudaError_t e = launch_conv_step(h, first, count, o, s, launches);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
+}
+
+cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches) {
+    if (h->cfg.S < 1) return cudaSuccess;
+    for (int o = 0; o < h->octaves; ++o) {
+        const OctGeom& g = h->oct[o];
+        const float* dog = frame_out(h, frame) + g.off + (size_t)(h->nl - 1) * g.plane;
+        unsigned char* flags = h->d_ext + (size_t)frame * h->ext_frame_bytes + g.ext_off;
+        const cudaError_t e = launch_extrema_octave(dog, flags, h->cfg.S, g.H, g.W, g.pitch, g.plane,
+                                                    h->cfg.extrema_thresh, h->stream);
+        if (e != cudaSuccess) return e;
+        ++*launches;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace sspyr

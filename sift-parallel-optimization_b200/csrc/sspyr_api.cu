@@ -248,6 +248,25 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
         return bail(e == cudaErrorMemoryAllocation ? SSPYR_ERR_NOMEM : SSPYR_ERR_CUDA,
                     std::string("cudaMalloc: ") + cudaGetErrorString(e));
     }
+    if (cfg.mode == SSPYR_MODE_CONV && banded) {
+        int rmax = 0;
+        for (int s2 = 0; s2 < nl; ++s2) rmax = h->conv[s2].radius > rmax ? h->conv[s2].radius : rmax;
+        h->halo_rmax = rmax;
+        size_t hf = 0;
+        for (int o = 0; o < h->octaves; ++o) {
+            if (h->oct[o].H < rmax)
+                return bail(SSPYR_ERR_ARG, "row band shorter than the blur radius at some octave (use fewer bands or octaves)");
+            h->halo_off[o] = hf;
+            hf += (size_t)2 * rmax * h->oct[o].pitch;
+        }
+        if ((e = dmalloc((void**)&h->d_halo, sizeof(float) * hf)) != cudaSuccess ||
+            (e = dmalloc((void**)&h->d_halo_raw, (size_t)2 * rmax * h->in_pitch_bytes)) != cudaSuccess ||
+            (e = cudaMemset(h->d_halo, 0, sizeof(float) * hf)) != cudaSuccess ||
+            (e = cudaMemset(h->d_halo_raw, 0, (size_t)2 * rmax * h->in_pitch_bytes)) != cudaSuccess) {
+            cudaGetLastError();
+            return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (halo): ") + cudaGetErrorString(e));
+        }
+    }
     if (cfg.outputs & SSPYR_OUT_EXTREMA) {
         if ((e = dmalloc((void**)&h->d_ext, h->ext_frame_bytes * cfg.frames)) != cudaSuccess) {
             cudaGetLastError();
@@ -271,6 +290,7 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
+    if (h->d_halo_raw) cudaFree(h->d_halo_raw);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaGetLastError();
@@ -354,11 +374,19 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
         for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
             e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
     } else {
-        for (int i = 0; i < count && e == cudaSuccess; ++i) {
-            e = launch_conv(h, (first + i) % h->cfg.frames, &launches);
-            if (e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA))
-                e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
+        if (h->cfg.full_height != h->cfg.height)
+            return fail(h, SSPYR_ERR_STATE, "a row-band CONV handle is driven level by level: sspyr_conv_step + halo exchange");
+        int done = 0;
+        while (done < count && e == cudaSuccess) {           // contiguous own slots share one launch per level
+            const int f0 = (first + done) % h->cfg.frames;
+            int n = 1;
+            if (!h->ext_in[f0])
+                while (done + n < count && f0 + n < h->cfg.frames && !h->ext_in[f0 + n]) ++n;
+            e = launch_conv(h, f0, n, &launches);
+            done += n;
         }
+        for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
+            e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
     }
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
     if (h->tune.timing) CU(h, cudaEventRecord(h->ev1, h->stream));
@@ -531,6 +559,62 @@ int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* ra
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemcpy(dst, h->d_tables + h->conv[level].taps_off, sizeof(float) * (2 * R + 1), cudaMemcpyDeviceToHost));
     if (radius) *radius = R;
+    return SSPYR_OK;
+}
+
+int sspyr_halo_rows(sspyr_handle h, int octave, int level, int* rows) {
+    if (!h || !rows) return SSPYR_ERR_ARG;
+    if (h->cfg.mode != SSPYR_MODE_CONV) { *rows = 0; return SSPYR_OK; }   // REF mode is pointwise: radius 0
+    if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "bad (octave, level)");
+    *rows = (level == 0 && octave > 0) ? 0 : h->conv[level].radius;
+    return SSPYR_OK;
+}
+
+int sspyr_halo_ptrs(sspyr_handle h, int frame, int octave, int level, void** send_up, void** send_down,
+                    void** recv_up, void** recv_down, size_t* bytes) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (h->cfg.mode != SSPYR_MODE_CONV || !h->d_halo) return fail(h, SSPYR_ERR_STATE, "not a row-band CONV handle");
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "bad (octave, level)");
+    if (level == 0 && octave > 0) return fail(h, SSPYR_ERR_ARG, "level 0 of octave > 0 is a decimation: no halo");
+    const int R = h->conv[level].radius;
+    const OctGeom& g = h->oct[octave];
+    if (level == 0) {                                        // the raw frame feeds (0, 0)
+        if (h->ext_in[frame]) return fail(h, SSPYR_ERR_UNSUPPORTED, "row-band CONV needs the frame in the handle's own slot (sspyr_upload)");
+        unsigned char* in = h->d_in + (size_t)frame * h->in_frame_bytes;
+        if (send_up) *send_up = in;
+        if (send_down) *send_down = in + (size_t)(h->cfg.height - R) * h->in_pitch_bytes;
+        if (recv_up) *recv_up = conv_halo_raw(h, 0);
+        if (recv_down) *recv_down = conv_halo_raw(h, 1);
+        if (bytes) *bytes = (size_t)R * h->in_pitch_bytes;
+    } else {
+        float* src = frame_out(h, frame) + g.off + (size_t)plane_index(h->nl, SSPYR_KIND_GAUSS, level - 1) * g.plane;
+        if (send_up) *send_up = src;
+        if (send_down) *send_down = src + (size_t)(g.H - R) * g.pitch;
+        if (recv_up) *recv_up = conv_halo_plane(h, octave, 0);
+        if (recv_down) *recv_down = conv_halo_plane(h, octave, 1);
+        if (bytes) *bytes = sizeof(float) * (size_t)R * g.pitch;
+    }
+    return SSPYR_OK;
+}
+
+int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
+    if (!h) return SSPYR_ERR_ARG;
+    if (h->cfg.mode != SSPYR_MODE_CONV) return fail(h, SSPYR_ERR_STATE, "sspyr_conv_step is for CONV mode");
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "bad (octave, level)");
+    CU(h, cudaSetDevice(h->device));
+    int launches = 0;
+    const cudaError_t e = launch_conv_step(h, frame, 1, octave, level, &launches);
+    if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
+    h->last_launches = launches;
+    if (octave == h->octaves - 1 && level == h->nl - 1) {
+        if (h->cfg.outputs & SSPYR_OUT_EXTREMA) {
+            const cudaError_t e2 = launch_extrema(h, frame, &launches);
+            if (e2 != cudaSuccess) return fail_cuda(h, e2, "kernel launch");
+        }
+        h->built[frame] = 1;
+    }
     return SSPYR_OK;
 }
 

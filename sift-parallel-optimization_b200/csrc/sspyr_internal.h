@@ -81,8 +81,10 @@ struct sspyr_ctx {
     float* d_tables = nullptr;
     std::vector<float> h_tables;
     std::vector<sspyr::ConvLevel> conv;      // per level
-    float* d_halo = nullptr;                 // CONV row-band halo receive buffers
-    size_t halo_floats = 0;
+    float* d_halo = nullptr;                 // CONV row-band halo receive buffers: per octave [up|down][rmax][pitch]
+    size_t halo_off[SSPYR_MAX_OCTAVES] = {0};
+    unsigned char* d_halo_raw = nullptr;     // same for the raw frame (octave 0, level 0): [up|down][rmax][in_pitch]
+    int halo_rmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     int last_launches = 0;
@@ -95,8 +97,12 @@ namespace sspyr {
 
 // Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
 cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
-cudaError_t launch_conv(const sspyr_ctx* h, int frame, int* launches);
-cudaError_t launch_conv_step(const sspyr_ctx* h, int frame, int octave, int level, int* launches);
+cudaError_t launch_conv(const sspyr_ctx* h, int first_frame, int count, int* launches);
+cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, int* launches);
+bool conv_has_up(const sspyr_ctx* h);
+bool conv_has_down(const sspyr_ctx* h);
+float* conv_halo_plane(const sspyr_ctx* h, int octave, int down);
+unsigned char* conv_halo_raw(const sspyr_ctx* h, int down);
 cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches);
 
 inline const unsigned char* frame_input(const sspyr_ctx* h, int frame, size_t* pitch_bytes) {

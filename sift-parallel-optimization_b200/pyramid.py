@@ -177,6 +177,22 @@ class ScaleSpace:
         self._ck(self._lib.sspyr_window_table(self._h, octave, level, axis, C.c_void_p(out.ctypes.data), out.size))
         return out
 
+    # ---- CONV mode, level by level (row bands: exchange halos between the steps) ----------------------
+    def halo_rows(self, octave: int, level: int) -> int:
+        r = C.c_int()
+        self._ck(self._lib.sspyr_halo_rows(self._h, octave, level, C.byref(r)))
+        return r.value
+
+    def halo_ptrs(self, octave: int, level: int, frame: int = 0) -> tuple[int, int, int, int, int]:
+        """(send_up, send_down, recv_up, recv_down, nbytes) device pointers for the halo of (octave, level)."""
+        p = [C.c_void_p() for _ in range(4)]
+        n = C.c_size_t()
+        self._ck(self._lib.sspyr_halo_ptrs(self._h, frame, octave, level, *[C.byref(x) for x in p], C.byref(n)))
+        return p[0].value, p[1].value, p[2].value, p[3].value, n.value
+
+    def conv_step(self, octave: int, level: int, frame: int = 0) -> None:
+        self._ck(self._lib.sspyr_conv_step(self._h, frame, octave, level))
+
     def conv_taps(self, level: int) -> np.ndarray:
         buf = np.empty(2 * 64 + 1, dtype=np.float32)
         R = C.c_int()

@@ -1,0 +1,148 @@
+"""GPU suite, CONV mode: the true separable-blur scale space (north_star) against its CPU specification
+(oracle/sspyr_oracle.c orc_conv_build).  There is no upstream parity for this mode -- the reference has no
+convolution -- so the bar is the north_star's tolerance against OUR restated oracle: max abs error <= 1e-4 of
+full scale per level (pixels 0..255 -> 0.0255; [0,1] floats -> 1e-4); level/DoG counts, dims, DoG order and
+decimation phase follow the reference (GuassDePyramid.h:64,66,80,140,143) and are exact."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def check(got, want, scale, what):
+    for o, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape, (what, o, a.shape, b.shape)
+        err = np.max(np.abs(a.astype(np.float64) - b.astype(np.float64)), axis=(1, 2))
+        assert np.all(err <= TOL * scale), f"{what} octave {o}: per-level max abs error {err} > {TOL * scale}"
+
+
+def test_taps_equal_the_specification(pkg, O):
+    for S, sigma0, rs in ((3, 1.6, 3.0), (3, 1.6, 4.0), (2, 1.2, 3.0), (5, 2.0, 3.0)):
+        with pkg.ScaleSpace(64, 64, 2, S, sigma0=sigma0, mode=pkg.MODE_CONV, radius_sigmas=rs) as ss:
+            for s in range(S + 3):
+                np.testing.assert_array_equal(ss.conv_taps(s), O.conv_taps(s, S, sigma0, 0.5, rs))
+
+
+@pytest.mark.parametrize("h,w,octs,S,rs", [(270, 480, 5, 3, 3.0), (135, 241, 3, 3, 3.0), (1080, 1920, 5, 3, 3.0),
+                                           (200, 333, 4, 3, 4.0), (96, 128, 3, 2, 3.0), (64, 70, 2, 5, 4.0),
+                                           (40, 1000, 3, 2, 3.0)])
+def test_full_pyramid_within_tolerance(pkg, O, synth, h, w, octs, S, rs):
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, S, radius_sigmas=rs)
+    with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs) as ss:
+        assert (ss.octaves, ss.levels, ss.dogs) == (octs, S + 3, S + 2)
+        ss.upload(img)
+        ss.build()
+        gg, dd = ss.download_gauss(), ss.download_dog()
+        for o in range(octs):
+            assert ss.level_dims(o)[:2] == (h >> o, w >> o)
+        check(gg, ref["gauss"], 255.0, "gauss")
+        check(dd, ref["dog"], 255.0, "dog")
+        for o in range(1, octs):            # exact: next octave base = even-phase decimation of G_S
+            np.testing.assert_array_equal(gg[o][0], gg[o - 1][S][::2, ::2][:h >> o, :w >> o])
+        for o in range(octs):               # exact up to the fused subtraction's own rounding
+            np.testing.assert_allclose(dd[o], gg[o][:-1] - gg[o][1:], atol=1e-5 * 255)
+
+
+def test_pixel_types_sigma_and_constant_image(pkg, O, synth):
+    h, w, octs = 150, 260, 4
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, 3, sigma0=2.0, sigma_in=0.0)
+    for pix, arr, scale in ((pkg.PIXEL_U8, img.astype(np.uint8), 255.0), (pkg.PIXEL_I32, img, 255.0)):
+        with pkg.ScaleSpace(h, w, octs, 3, sigma0=2.0, sigma_in=0.0, mode=pkg.MODE_CONV, pixel_type=pix) as ss:
+            ss.upload(arr)
+            ss.build()
+            check(ss.download_gauss(), ref["gauss"], scale, f"gauss pix{pix}")
+    norm = (img / 255.0).astype(np.float32)
+    fref = O.conv_build(norm, octs, 3)
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, pixel_type=pkg.PIXEL_F32) as ss:
+        ss.upload(norm)
+        ss.build()
+        check(ss.download_gauss(), fref["gauss"], 1.0, "gauss f32")       # the north_star's 1e-4 on [0,1] pixels
+        check(ss.download_dog(), fref["dog"], 1.0, "dog f32")
+    const = np.full((h, w), 9, dtype=np.int32)
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV) as ss:
+        ss.upload(const)
+        ss.build()
+        for g in ss.download_gauss():
+            np.testing.assert_allclose(g, 9.0, rtol=2e-6)                  # DC gain 1 with clamp-to-edge borders
+
+
+def test_batched_frame_slots(pkg, O, synth):
+    h, w, octs, n = 120, 200, 3, 4
+    frames = [synth.noise(h, w, frame=f) for f in range(n)]
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n) as ss:
+        for f in range(n):
+            ss.upload(frames[f], frame=f)
+        ss.build_batch(0, n)
+        assert ss.last_launches() == 6 + 5 * (octs - 1)      # one launch per level for the whole batch
+        for f in (0, 3):
+            check(ss.download_gauss(frame=f), O.conv_build(frames[f], octs, 3)["gauss"], 255.0, f"frame {f}")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_bands_with_halo_exchange(pkg, O, synth, world):
+    """ROWBAND partition emulated on one GPU: one handle per band, neighbour halo rows copied before every
+    level (LocalExchanger -- the same schedule DistExchanger runs over NCCL)."""
+    h, w, octs, S = 416, 300, 4, 3
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, S)
+    bands = [pkg.band_rows(h, octs, world, r) for r in range(world)]
+    hs = []
+    for row0, rows in bands:
+        ss = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, band_row0=row0, full_height=h)
+        ss.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+        hs.append(ss)
+    with pytest.raises(pkg.SspyrError):
+        hs[0].build()                                         # banded CONV must go level by level
+    pkg.LocalExchanger(hs).build()
+    for (row0, rows), ss in zip(bands, hs):
+        gg, dd = ss.download_gauss(), ss.download_dog()
+        want_g = [ref["gauss"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)]
+        want_d = [ref["dog"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)]
+        check(gg, want_g, 255.0, f"band@{row0} gauss")
+        check(dd, want_d, 255.0, f"band@{row0} dog")
+        ss.close()
+
+
+def test_bands_match_the_unbanded_gpu_result_exactly(pkg, synth):
+    """Same kernels, same summation order: a banded build must equal the single-handle build bit for bit."""
+    h, w, octs, S = 256, 200, 3, 3
+    img = synth.noise(h, w)
+    with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV) as ss:
+        ss.upload(img)
+        ss.build()
+        whole = ss.download_gauss()
+    hs = []
+    for r in range(2):
+        row0, rows = pkg.band_rows(h, octs, 2, r)
+        b = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, band_row0=row0, full_height=h)
+        b.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+        hs.append((row0, rows, b))
+    pkg.LocalExchanger([b for _, _, b in hs]).build()
+    for row0, rows, b in hs:
+        for o, g in enumerate(b.download_gauss()):
+            np.testing.assert_array_equal(g, whole[o][:, row0 >> o:(row0 >> o) + (rows >> o)])
+        b.close()
+
+
+def test_extrema_flags(pkg, O, synth):
+    h, w, octs, S = 96, 128, 3, 3
+    img = synth.noise(h, w)
+    for mode in (pkg.MODE_CONV, pkg.MODE_REF):
+        with pkg.ScaleSpace(h, w, octs, S, mode=mode, outputs=pkg.OUT_ALL | pkg.OUT_EXTREMA, extrema_thresh=0.5) as ss:
+            ss.upload(img)
+            ss.build()
+            dd = ss.download_dog()
+            total = 0
+            for o in range(octs):
+                want = O.extrema_octave(dd[o], 0.5)              # scan of the GPU's own DoG planes: exact
+                got = np.stack([ss.download(o, s, pkg.KIND_EXTREMA) for s in range(S)])
+                np.testing.assert_array_equal(got, want)
+                total += int(want.sum())
+            if mode == pkg.MODE_CONV:
+                assert total > 0
