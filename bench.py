@@ -248,10 +248,18 @@ def run_native(args) -> dict:
 
     launches = [0]
     cursor = [0]
+    exchanger = None
+    if ss is not None and args.mode == "conv" and part == "rowband" and world > 1:
+        exchanger = pkg.DistExchanger(ss, rank, world, torch.device("cuda", local))
 
     def step():
         """One pass over this rank's share of the batch: my_frames frames through the slot ring."""
         if ss is None:
+            return
+        if exchanger is not None:            # CONV row bands: per-level neighbour halo exchange over NCCL P2P
+            exchanger.build(cursor[0])
+            launches[0] += conv_launches
+            cursor[0] = (cursor[0] + 1) % slots
             return
         left = my_frames
         while left:
@@ -261,6 +269,7 @@ def run_native(args) -> dict:
             cursor[0] = (cursor[0] + n) % slots
             left -= n
 
+    conv_launches = ss.levels + (ss.levels - 1) * (ss.octaves - 1) if ss is not None else 0
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -285,7 +294,16 @@ def run_native(args) -> dict:
     my_launches = launches[0]
     # roofline of the dominant (only) kernel on this rank: algorithmic bytes per launch / mean launch time
     peak, peak_src = measured_peak()
-    bytes_per_launch = frame_bytes * my_frames * steps / max(my_launches, 1)
+    work_bytes = frame_bytes
+    if args.mode == "conv" and ss is not None:
+        # per-level design traffic: every level kernel reads its input plane once and writes G_s (+ DoG_{s-1},
+        # + the decimated base of the next octave): 12 B per level-pixel, vs B_full's 4*(2S+5) per octave pixel
+        px = [ss.level_dims(o)[0] * ss.level_dims(o)[1] for o in range(ss.octaves)]
+        nl = ss.levels
+        work_bytes = rows * width * (1 if ss.pixel_type == pkg.PIXEL_U8 else 4) + 4 * px[0] * (nl + nl - 1 + nl - 1)
+        for o in range(1, ss.octaves):
+            work_bytes += 4 * px[o] * (1 + (nl - 1) * 3)
+    bytes_per_launch = work_bytes * my_frames * steps / max(my_launches, 1)
     launch_ms = my_ms / max(my_launches, 1)
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if my_launches else 0.0
     achieved = dist.sum(achieved) / world                                      # mean per-GPU achieved GB/s
@@ -313,7 +331,10 @@ def run_native(args) -> dict:
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "launch_us": round(launch_ms * 1e3, 3),
-                     "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_*"},
+                     "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_level_kernel",
+                     "bytes_model": "B_full: input read once + every output plane written once" if args.mode == "ref"
+                     else "per-level: input plane read + G_s, DoG_{s-1}, decimated base written, summed over the level launches",
+                     "b_full_frac": round(frame_bytes * my_frames * steps / (my_ms * 1e-3) / 1e9 / peak, 4) if my_ms else None},
         "clocks": clocks,
     }
     if e2e:

@@ -19,8 +19,9 @@ cudaError_t launch_extrema_octave(const float* dog, unsigned char* flags, int S,
     return cudaGetLastError();
 }
 #else
-cudaError_t SSPYR_CAT(launch_conv_r, SSPYR_R)(const ConvParams& P, int src_kind, dim3 grid, cudaStream_t st, int device) {
-    return launch_conv_src<SSPYR_R>(P, src_kind, grid, st, device);
+cudaError_t SSPYR_CAT(launch_conv_r, SSPYR_R)(const ConvParams& P, int src_kind, int variant, cudaStream_t st, int device,
+                                              int frames, int sms) {
+    return launch_conv_src<SSPYR_R>(P, src_kind, variant, st, device, frames, sms);
 }
 #endif
 }  // namespace sspyr

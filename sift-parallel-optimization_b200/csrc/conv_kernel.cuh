@@ -13,7 +13,9 @@
 // so every level is read from HBM/L2 exactly once and written once; DoG and the next octave's base never
 // cost a separate pass.
 //
-//   * CTA tile TW x TH = 128 x 64 (128 x 32 for wide kernels) outputs, 256 threads.
+//   * CTA tile TW x TH = 128 x 32 outputs, 256 threads, 3-4 CTAs resident per SM so that one CTA's cp.async
+//     staging overlaps its neighbours' filtering.  (Also built, selectable and measured slower: 64-row tiles;
+//     persistent CTAs that double-buffer the staging tile.)
 //   * Row pass: a thread owns 16 consecutive outputs of one row; lanes of a warp take consecutive ROWS and
 //     the smem pitch is 4*odd floats, so its 128-bit smem loads/stores are bank-conflict free.
 //   * Column pass: a thread owns 4 adjacent columns x (TH/8) rows and slides down the rows, holding the
@@ -53,14 +55,14 @@ struct ConvParams {
 };
 
 template <int R> __host__ __device__ constexpr int conv_ra() { return (R + 3) / 4 * 4; }          // aligned halo
-template <int R> __host__ __device__ constexpr int conv_th() { return R <= 10 ? 64 : 32; }
+template <int R> __host__ __device__ constexpr int conv_th_max() { return R <= 6 ? 64 : 32; }   // tallest tile that keeps 2 CTAs/SM
 template <int R> __host__ __device__ constexpr int conv_pitch_in() {                            // 4 * odd
     int q = (CONV_TW + 2 * conv_ra<R>()) / 4;
     return 4 * (q | 1);
 }
 __host__ __device__ constexpr int conv_pitch_t() { return 4 * ((CONV_TW / 4) | 1); }             // 132
-template <int R> __host__ __device__ constexpr size_t conv_smem_bytes() {
-    return sizeof(float) * (size_t)(conv_th<R>() + 2 * R) * (conv_pitch_in<R>() + conv_pitch_t());
+template <int R, int TH, int NBUF> __host__ __device__ constexpr size_t conv_smem_bytes() {   // staging buffer(s) + sT
+    return sizeof(float) * (size_t)(TH + 2 * R) * (NBUF * conv_pitch_in<R>() + conv_pitch_t());
 }
 
 namespace {
@@ -72,145 +74,205 @@ __device__ __forceinline__ float load_src(const void* __restrict__ base, size_t 
     else return __ldg(static_cast<const float*>(base) + idx);
 }
 
-template <int R, int SRC>
-__global__ void __launch_bounds__(CONV_THREADS, 2)
-conv_level_kernel(const __grid_constant__ ConvParams P) {
+// Stage one tile (centre + halo) of frame fz into sIn: clamp to edge, or the neighbour's halo rows for a band.
+// Interior tiles of a float plane go through cp.async (no registers, completion tracked by the pipeline);
+// everything else is loaded, converted and stored synchronously.
+template <int R, int SRC, int TH>
+__device__ __forceinline__ void conv_stage_tile(const ConvParams& P, float* __restrict__ sIn, int x0, int y0, size_t fz,
+                                                int tid) {
     constexpr int RA = conv_ra<R>();
-    constexpr int TH = conv_th<R>();
-    constexpr int ROWS = TH + 2 * R;              // rows of the staged tile
+    constexpr int ROWS = TH + 2 * R;
     constexpr int PIN = conv_pitch_in<R>();
-    constexpr int PT = conv_pitch_t();
-    constexpr int COLS = CONV_TW + 2 * RA;        // staged columns
-    constexpr int PY = TH / 8;                    // rows per thread in the column pass
-    extern __shared__ __align__(16) float smem[];
-    float* sIn = smem;                            // [ROWS][PIN]  input tile + halo (centre starts at column RA)
-    float* sT = smem + (size_t)ROWS * PIN;        // [ROWS][PT]   row-pass result
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * CONV_TW;
-    const int y0 = blockIdx.y * TH;
-    const size_t fz = blockIdx.z;
-    const int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
+    constexpr int COLS = CONV_TW + 2 * RA;
+    constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
     const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
-
-    // ---- stage the tile: global -> shared, clamp to edge (or neighbour halo rows for a band) ---------
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        const bool fast_x = SRC == CONV_SRC_PLANE && x0 - RA >= 0 && x0 + CONV_TW + RA <= P.W;
-        for (int ly = warp; ly < ROWS; ly += CONV_THREADS / 32) {
-            const int gy = y0 - R + ly;
-            const unsigned char* row;
-            if (gy < 0) {
-                row = P.top_halo ? static_cast<const unsigned char*>(P.top_halo) + (size_t)(P.halo_rows + gy) * P.src_pitch * elem
-                                 : src;
-                if (P.top_halo && P.halo_rows + gy < 0) row = static_cast<const unsigned char*>(P.top_halo);
-            } else if (gy >= P.H) {
-                const int k = gy - P.H;
-                row = P.bot_halo ? static_cast<const unsigned char*>(P.bot_halo) + (size_t)min(k, P.halo_rows - 1) * P.src_pitch * elem
-                                 : src + (size_t)(P.H - 1) * P.src_pitch * elem;
-            } else {
-                row = src + (size_t)gy * P.src_pitch * elem;
-            }
-            float* srow = sIn + (size_t)ly * PIN;
-            if (fast_x) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const bool fast_x = x0 - RA >= 0 && x0 + CONV_TW + RA <= P.W;   // whole staged span inside the row: 128-bit path
+    for (int ly = warp; ly < ROWS; ly += CONV_THREADS / 32) {
+        const int gy = y0 - R + ly;
+        const unsigned char* row;
+        if (gy < 0) {
+            row = P.top_halo ? static_cast<const unsigned char*>(P.top_halo) + (size_t)max(P.halo_rows + gy, 0) * P.src_pitch * elem
+                             : src;
+        } else if (gy >= P.H) {
+            row = P.bot_halo ? static_cast<const unsigned char*>(P.bot_halo) + (size_t)min(gy - P.H, P.halo_rows - 1) * P.src_pitch * elem
+                             : src + (size_t)(P.H - 1) * P.src_pitch * elem;
+        } else {
+            row = src + (size_t)gy * P.src_pitch * elem;
+        }
+        float* srow = sIn + (size_t)ly * PIN;
+        if (fast_x) {
+            if constexpr (SRC == CONV_SRC_PLANE) {
                 const float* grow = reinterpret_cast<const float*>(row) + (x0 - RA);
                 for (int q = lane; q < COLS / 4; q += 32) __pipeline_memcpy_async(srow + 4 * q, grow + 4 * q, 16);
             } else {
-                for (int lx = lane; lx < COLS; lx += 32) {
-                    const int gx = min(max(x0 - RA + lx, 0), P.W - 1);
-                    srow[lx] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(row, (size_t)gx);
+                for (int q = lane; q < COLS / 4; q += 32) {
+                    float4 v;
+                    if constexpr (SRC == SSPYR_PIXEL_I32) {
+                        const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(row) + (x0 - RA)) + q);
+                        v = make_float4((float)t.x, (float)t.y, (float)t.z, (float)t.w);
+                    } else if constexpr (SRC == SSPYR_PIXEL_U8) {
+                        const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(row + (x0 - RA)) + q);
+                        v = make_float4((float)t.x, (float)t.y, (float)t.z, (float)t.w);
+                    } else {
+                        v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + (x0 - RA)) + q);
+                    }
+                    *reinterpret_cast<float4*>(srow + 4 * q) = v;
                 }
             }
-        }
-        __pipeline_commit();
-        __pipeline_wait_prior(0);
-    }
-    __syncthreads();
-
-    // ---- row pass: sT[row][c] = sum_k taps[k] * sIn[row][RA + c + k] ------------------------------------
-    {
-        constexpr int NB = CONV_TW / CONV_PX;                 // column blocks per row
-        constexpr int NIN = CONV_PX + 2 * RA;                 // aligned input window per task
-        for (int task = tid; task < ROWS * NB; task += CONV_THREADS) {
-            const int row = task % ROWS, cb = task / ROWS;    // consecutive lanes -> consecutive rows
-            const float4* in4 = reinterpret_cast<const float4*>(sIn + (size_t)row * PIN + cb * CONV_PX);
-            float in[NIN];
-#pragma unroll
-            for (int q = 0; q < NIN / 4; ++q) {
-                const float4 v = in4[q];
-                in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        } else {
+            for (int lx = lane; lx < COLS; lx += 32) {
+                const int gx = min(max(x0 - RA + lx, 0), P.W - 1);
+                srow[lx] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(row, (size_t)gx);
             }
-            float acc[CONV_PX];
-#pragma unroll
-            for (int i = 0; i < CONV_PX; ++i) {
-                float a = 0.0f;
-#pragma unroll
-                for (int k = 0; k <= 2 * R; ++k) a = fmaf(P.taps[k], in[i + k + (RA - R)], a);
-                acc[i] = a;
-            }
-            float4* out4 = reinterpret_cast<float4*>(sT + (size_t)row * PT + cb * CONV_PX);
-#pragma unroll
-            for (int q = 0; q < CONV_PX / 4; ++q) out4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
         }
     }
-    __syncthreads();
+}
 
-    // ---- column pass + epilogue -------------------------------------------------------------------------
-    {
-        const int cq = tid & 31, rb = tid >> 5;              // column quad, row block
-        const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
-        float acc[PY][4];
+// CTAs walk the tile list (tile = blockIdx.x, += gridDim.x; x fastest, then y, then frame).
+//   NBUF == 1: one tile per CTA (grid = ntiles), single staging buffer -- more CTAs resident per SM.
+//   NBUF == 2: persistent CTAs with a two-deep software pipeline -- while tile i is filtered out of one staging
+//              buffer the cp.async loads of tile i+1 land in the other (measured slower on B200: the second
+//              buffer costs a resident CTA per SM, see profiles/).
+template <int R, int SRC, int TH, int NBUF>
+__global__ void __launch_bounds__(CONV_THREADS, 2)
+conv_level_kernel(const __grid_constant__ ConvParams P, int tiles_x, int tiles_y, int ntiles) {
+    constexpr int RA = conv_ra<R>();
+    constexpr int ROWS = TH + 2 * R;              // rows of the staged tile
+    constexpr int PIN = conv_pitch_in<R>();
+    constexpr int PT = conv_pitch_t();
+    constexpr int PY = TH / 8;                    // rows per thread in the column pass
+    extern __shared__ __align__(16) float smem[];
+    constexpr int BUF = ROWS * PIN;                         // [ROWS][PIN] x 2: input tile + halo (centre at column RA)
+    float* sT = smem + (size_t)NBUF * ROWS * PIN;           // [ROWS][PT]: row-pass result
+
+    const int tid = threadIdx.x;
+    int tile = blockIdx.x;
+    if (tile >= ntiles) return;
+    auto coords = [&](int t, int& x0, int& y0, size_t& fz) {
+        const int tx = t % tiles_x, r = t / tiles_x;
+        x0 = tx * CONV_TW;
+        y0 = (r % tiles_y) * TH;
+        fz = (size_t)(r / tiles_y);
+    };
+    int x0, y0;
+    size_t fz;
+    coords(tile, x0, y0, fz);
+    conv_stage_tile<R, SRC, TH>(P, smem, x0, y0, fz, tid);
+    __pipeline_commit();
+    int cur = 0;
+    for (; tile < ntiles; tile += gridDim.x, cur ^= 1) {
+        const int next = tile + gridDim.x;
+        if constexpr (NBUF == 2) {
+            if (next < ntiles) {                               // prefetch the next tile into the other buffer
+                int nx, ny;
+                size_t nf;
+                coords(next, nx, ny, nf);
+                conv_stage_tile<R, SRC, TH>(P, smem + (cur ^ 1) * BUF, nx, ny, nf, tid);
+            }
+            __pipeline_commit();
+            __pipeline_wait_prior(1);                          // everything but the newest group has landed
+        } else {
+            __pipeline_wait_prior(0);
+        }
+        __syncthreads();
+        const float* sIn = smem + (NBUF == 2 ? cur : 0) * BUF;
+        coords(tile, x0, y0, fz);
+
+        // ---- row pass: sT[row][c] = sum_k taps[k] * sIn[row][RA + c + k] ---------------------------------
+        {
+            constexpr int NB = CONV_TW / CONV_PX;                 // column blocks per row
+            constexpr int NIN = CONV_PX + 2 * RA;                 // aligned input window per task
+            for (int task = tid; task < ROWS * NB; task += CONV_THREADS) {
+                const int row = task % ROWS, cb = task / ROWS;    // consecutive lanes -> consecutive rows
+                const float4* in4 = reinterpret_cast<const float4*>(sIn + (size_t)row * PIN + cb * CONV_PX);
+                float in[NIN];
 #pragma unroll
-        for (int j = 0; j < PY; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
-#pragma unroll
-        for (int i = 0; i < PY + 2 * R; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
-#pragma unroll
-            for (int j = 0; j < PY; ++j) {
-                if (i - j >= 0 && i - j <= 2 * R) {            // compile-time after unrolling
-                    const float w = P.taps[i - j];
-                    acc[j][0] = fmaf(w, v.x, acc[j][0]);
-                    acc[j][1] = fmaf(w, v.y, acc[j][1]);
-                    acc[j][2] = fmaf(w, v.z, acc[j][2]);
-                    acc[j][3] = fmaf(w, v.w, acc[j][3]);
+                for (int q = 0; q < NIN / 4; ++q) {
+                    const float4 v = in4[q];
+                    in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
                 }
+                float acc[CONV_PX];
+#pragma unroll
+                for (int i = 0; i < CONV_PX; ++i) acc[i] = 0.0f;
+#pragma unroll
+                for (int k = 0; k <= 2 * R; ++k) {                 // taps outer: 16 independent FMA chains in flight
+                    const float w = P.taps[k];
+#pragma unroll
+                    for (int i = 0; i < CONV_PX; ++i) acc[i] = fmaf(w, in[i + k + (RA - R)], acc[i]);
+                }
+                float4* out4 = reinterpret_cast<float4*>(sT + (size_t)row * PT + cb * CONV_PX);
+#pragma unroll
+                for (int q = 0; q < CONV_PX / 4; ++q) out4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
             }
         }
-        const int x = x0 + cq * 4;
-        if (x < P.W) {
-            const int nvalid = P.W - x;
-            float* g = P.dst_g + fz * P.dst_frame_stride;
-            float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
-            float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
+        __syncthreads();
+
+        // ---- column pass + epilogue -------------------------------------------------------------------------
+        {
+            const int cq = tid & 31, rb = tid >> 5;              // column quad, row block
+            const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
+            float acc[PY][4];
 #pragma unroll
-            for (int j = 0; j < PY; ++j) {
-                const int y = y0 + rb * PY + j;
-                if (y >= P.H) break;
-                const size_t o = (size_t)y * P.dst_pitch + x;
-                if (nvalid >= 4) {
-                    *reinterpret_cast<float4*>(g + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                } else {
+            for (int j = 0; j < PY; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) if (i < nvalid) g[o + i] = acc[j][i];
+            for (int i = 0; i < PY + 2 * R; ++i) {
+                const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    if (i - j >= 0 && i - j <= 2 * R) {            // compile-time after unrolling
+                        const float w = P.taps[i - j];
+                        acc[j][0] = fmaf(w, v.x, acc[j][0]);
+                        acc[j][1] = fmaf(w, v.y, acc[j][1]);
+                        acc[j][2] = fmaf(w, v.z, acc[j][2]);
+                        acc[j][3] = fmaf(w, v.w, acc[j][3]);
+                    }
                 }
-                if (d) {                                        // DoG_{s-1} = G_{s-1} - G_s  (GuassDePyramid.h:143)
-                    const float4 c = *reinterpret_cast<const float4*>(sIn + (size_t)(R + rb * PY + j) * PIN + RA + cq * 4);
-                    const float dv[4] = {c.x - acc[j][0], c.y - acc[j][1], c.z - acc[j][2], c.w - acc[j][3]};
+            }
+            const int x = x0 + cq * 4;
+            if (x < P.W) {
+                const int nvalid = P.W - x;
+                float* g = P.dst_g + fz * P.dst_frame_stride;
+                float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
+                float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
+#pragma unroll
+                for (int j = 0; j < PY; ++j) {
+                    const int y = y0 + rb * PY + j;
+                    if (y >= P.H) break;
+                    const size_t o = (size_t)y * P.dst_pitch + x;
                     if (nvalid >= 4) {
-                        __stcs(reinterpret_cast<float4*>(d + o), make_float4(dv[0], dv[1], dv[2], dv[3]));
+                        *reinterpret_cast<float4*>(g + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) if (i < nvalid) __stcs(d + o + i, dv[i]);
+                        for (int i = 0; i < 4; ++i) if (i < nvalid) g[o + i] = acc[j][i];
+                    }
+                    if (d) {                                        // DoG_{s-1} = G_{s-1} - G_s  (GuassDePyramid.h:143)
+                        const float4 c = *reinterpret_cast<const float4*>(sIn + (size_t)(R + rb * PY + j) * PIN + RA + cq * 4);
+                        const float dv[4] = {c.x - acc[j][0], c.y - acc[j][1], c.z - acc[j][2], c.w - acc[j][3]};
+                        if (nvalid >= 4) {
+                            __stcs(reinterpret_cast<float4*>(d + o), make_float4(dv[0], dv[1], dv[2], dv[3]));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) if (i < nvalid) __stcs(d + o + i, dv[i]);
+                        }
+                    }
+                    if (dec && (y & 1) == 0) {                      // even-phase decimation (GuassDePyramid.h:80)
+                        const int dy = y >> 1, dx = x >> 1;
+                        if (dy < P.dec_H && dx < P.dec_W) {
+                            float* q = dec + (size_t)dy * P.dec_pitch + dx;
+                            if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
+                            else q[0] = acc[j][0];
+                        }
                     }
                 }
-                if (dec && (y & 1) == 0) {                      // even-phase decimation (GuassDePyramid.h:80)
-                    const int dy = y >> 1, dx = x >> 1;
-                    if (dy < P.dec_H && dx < P.dec_W) {
-                        float* q = dec + (size_t)dy * P.dec_pitch + dx;
-                        if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
-                        else q[0] = acc[j][0];
-                    }
-                }
+            }
+        }
+        __syncthreads();        // sT and this staging buffer are free for the tile after next
+        if constexpr (NBUF == 1) {
+            if (next < ntiles) {
+                coords(next, x0, y0, fz);
+                conv_stage_tile<R, SRC, TH>(P, smem, x0, y0, fz, tid);
+                __pipeline_commit();
             }
         }
     }
@@ -246,26 +308,50 @@ extrema_kernel(const float* __restrict__ dog, unsigned char* __restrict__ flags,
     flags[(size_t)(s - 1) * plane + (size_t)r * pitch + c] = f;
 }
 
-template <int R, int SRC>
-cudaError_t launch_conv_one(const ConvParams& P, dim3 grid, cudaStream_t st, int device) {
-    constexpr size_t smem = conv_smem_bytes<R>();
+template <int R, int SRC, int TH, int NBUF>
+cudaError_t launch_conv_one(const ConvParams& P, cudaStream_t st, int device, int frames, int max_ctas) {
+    constexpr size_t smem = conv_smem_bytes<R, TH, NBUF>();
     static bool configured[64] = {false};         // the attribute is per device
     if (device < 0 || device >= 64 || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_level_kernel<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_level_kernel<R, SRC, TH, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) configured[device] = true;
     }
-    conv_level_kernel<R, SRC><<<grid, CONV_THREADS, smem, st>>>(P);
+    const int tiles_x = (P.W + CONV_TW - 1) / CONV_TW, tiles_y = (P.H + TH - 1) / TH;
+    const long long ntiles = (long long)tiles_x * tiles_y * frames;
+    if (ntiles > 0x7fffffffLL) return cudaErrorInvalidValue;
+    long long ctas = ntiles;
+    if (NBUF == 2) {    // persistent grid: as many CTAs as fit on the GPU at once (smem-limited), never more than tiles
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+        ctas = (long long)max_ctas * per_sm;
+        if (ctas > ntiles) ctas = ntiles;
+    }
+    conv_level_kernel<R, SRC, TH, NBUF><<<(unsigned)ctas, CONV_THREADS, smem, st>>>(P, tiles_x, tiles_y, (int)ntiles);
     return cudaGetLastError();
 }
 
+// tall: 64-row tiles (less row-pass halo overhead) when the level has enough tiles to fill the GPU; otherwise
+// 32-row tiles: twice the CTAs, more of them resident, shorter per-CTA latency.
+// variant: bit 0 = 64-row tiles (radii <= 6 only), bit 1 = persistent double-buffered pipeline (float planes only)
+template <int R, int SRC>
+cudaError_t launch_conv_th(const ConvParams& P, int variant, cudaStream_t st, int device, int frames, int sms) {
+    if constexpr (conv_th_max<R>() >= 64) {
+        if (variant & 1) return launch_conv_one<R, SRC, 64, 1>(P, st, device, frames, sms);
+    }
+    if constexpr (SRC == CONV_SRC_PLANE) {
+        if (variant & 2) return launch_conv_one<R, SRC, 32, 2>(P, st, device, frames, sms);
+    }
+    return launch_conv_one<R, SRC, 32, 1>(P, st, device, frames, sms);
+}
+
 template <int R>
-cudaError_t launch_conv_src(const ConvParams& P, int src_kind, dim3 grid, cudaStream_t st, int device) {
+cudaError_t launch_conv_src(const ConvParams& P, int src_kind, int variant, cudaStream_t st, int device, int frames, int sms) {
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_conv_one<R, SSPYR_PIXEL_I32>(P, grid, st, device);
-        case SSPYR_PIXEL_F32: return launch_conv_one<R, SSPYR_PIXEL_F32>(P, grid, st, device);
-        case SSPYR_PIXEL_U8: return launch_conv_one<R, SSPYR_PIXEL_U8>(P, grid, st, device);
-        default: return launch_conv_one<R, CONV_SRC_PLANE>(P, grid, st, device);
+        case SSPYR_PIXEL_I32: return launch_conv_th<R, SSPYR_PIXEL_I32>(P, variant, st, device, frames, sms);
+        case SSPYR_PIXEL_F32: return launch_conv_th<R, SSPYR_PIXEL_F32>(P, variant, st, device, frames, sms);
+        case SSPYR_PIXEL_U8: return launch_conv_th<R, SSPYR_PIXEL_U8>(P, variant, st, device, frames, sms);
+        default: return launch_conv_th<R, CONV_SRC_PLANE>(P, variant, st, device, frames, sms);
     }
 }
 

@@ -6,7 +6,7 @@
 
 namespace sspyr {
 
-#define SSPYR_DECL(n) cudaError_t launch_conv_r##n(const ConvParams&, int, dim3, cudaStream_t, int);
+#define SSPYR_DECL(n) cudaError_t launch_conv_r##n(const ConvParams&, int, int, cudaStream_t, int, int, int);
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_DECL(14) SSPYR_DECL(15) SSPYR_DECL(16)
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
@@ -18,9 +18,9 @@ namespace {
 // compiled radius that serves a requested one (taps are zero-padded up to it)
 int compiled_radius(int r) { return r <= 16 ? r : r <= 20 ? 20 : r <= 24 ? 24 : r <= 28 ? 28 : 32; }
 
-cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, dim3 grid, cudaStream_t st, int device) {
+cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cudaStream_t st, int device, int frames, int sms) {
     switch (rt) {
-#define SSPYR_CASE(n) case n: return launch_conv_r##n(P, src_kind, grid, st, device);
+#define SSPYR_CASE(n) case n: return launch_conv_r##n(P, src_kind, variant, st, device, frames, sms);
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12) SSPYR_CASE(13) SSPYR_CASE(14) SSPYR_CASE(15)
         SSPYR_CASE(16) SSPYR_CASE(20) SSPYR_CASE(24) SSPYR_CASE(28) SSPYR_CASE(32)
@@ -43,7 +43,8 @@ unsigned char* conv_halo_raw(const sspyr_ctx* h, int down) {
 }
 
 // The blur that PRODUCES (octave, level) for frame slots first..first+count-1 (contiguous, own input slots).
-cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octave, int level, int* launches) {
+cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octave, int level, cudaStream_t st,
+                             int* launches) {
     if (level == 0 && octave > 0) return cudaSuccess;      // written by the decimating epilogue of (octave-1, S)
     const int nl = h->nl, S = h->cfg.S;
     const OctGeom& g = h->oct[octave];
@@ -85,21 +86,40 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     }
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps + (RT - R), h->h_tables.data() + h->conv[level].taps_off, sizeof(float) * (2 * R + 1));
-    const int TH = RT <= 10 ? 64 : 32;
-    const dim3 grid((g.W + CONV_TW - 1) / CONV_TW, (g.H + TH - 1) / TH, count);
-    const cudaError_t e = dispatch(RT, P, src_kind, grid, h->stream, h->device);
+    const int variant = (h->tune.conv_tall > 0 ? 1 : 0) | (h->tune.conv_pipe > 0 ? 2 : 0);   // default: 32-row, one tile per CTA
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const cudaError_t e = dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     return e;
 }
 
 // Whole pyramid of one or more frame slots (no row bands: a banded handle is driven level by level so that the
-// host can exchange halos between steps).
+// host can exchange halos between steps).  Octaves run concurrently: octave o+1 only depends on level S of octave o
+// (its decimated base), so each octave gets its own stream, forked from the handle's stream by events and joined
+// back at the end -- the small octaves' short kernels hide behind the large ones instead of queueing after them.
 cudaError_t launch_conv(const sspyr_ctx* h, int first, int count, int* launches) {
-    for (int o = 0; o < h->octaves; ++o)
+    const int S = h->cfg.S;
+    const bool fork = h->tune.conv_streams != 0 && h->octaves > 1 && !h->aux.empty();
+    cudaError_t e;
+    if (!fork) {
+        for (int o = 0; o < h->octaves; ++o)
+            for (int s = 0; s < h->nl; ++s)
+                if ((e = launch_conv_step(h, first, count, o, s, h->stream, launches)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    for (int o = 0; o < h->octaves; ++o) {
+        cudaStream_t st = o == 0 ? h->stream : h->aux[o - 1];
+        if (o > 0 && (e = cudaStreamWaitEvent(st, h->ev_base[o - 1], 0)) != cudaSuccess) return e;   // base of octave o ready
         for (int s = 0; s < h->nl; ++s) {
-            const cudaError_t e = launch_conv_step(h, first, count, o, s, launches);
-            if (e != cudaSuccess) return e;
+            if ((e = launch_conv_step(h, first, count, o, s, st, launches)) != cudaSuccess) return e;
+            if (s == S && o + 1 < h->octaves && (e = cudaEventRecord(h->ev_base[o], st)) != cudaSuccess) return e;
         }
+        if (o > 0) {                                            // join
+            if ((e = cudaEventRecord(h->ev_done[o - 1], st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(h->stream, h->ev_done[o - 1], 0)) != cudaSuccess) return e;
+        }
+    }
     return cudaSuccess;
 }
 

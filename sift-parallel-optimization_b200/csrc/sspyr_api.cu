@@ -278,6 +278,16 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
         (e = cudaMemset(h->d_in, 0, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
         (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess)
         return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    if (cfg.mode == SSPYR_MODE_CONV && h->octaves > 1) {
+        h->aux.assign(h->octaves - 1, nullptr);
+        h->ev_base.assign(h->octaves - 1, nullptr);
+        h->ev_done.assign(h->octaves - 1, nullptr);
+        for (int o = 0; o + 1 < h->octaves; ++o)
+            if ((e = cudaStreamCreateWithFlags(&h->aux[o], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_base[o], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&h->ev_done[o], cudaEventDisableTiming)) != cudaSuccess)
+                return bail(SSPYR_ERR_CUDA, std::string("stream setup: ") + cudaGetErrorString(e));
+    }
     *out = h;
     return SSPYR_OK;
 }
@@ -291,6 +301,9 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
+    for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : h->ev_done) if (ev) cudaEventDestroy(ev);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     cudaGetLastError();
@@ -605,7 +618,7 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
     if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "bad (octave, level)");
     CU(h, cudaSetDevice(h->device));
     int launches = 0;
-    const cudaError_t e = launch_conv_step(h, frame, 1, octave, level, &launches);
+    const cudaError_t e = launch_conv_step(h, frame, 1, octave, level, h->stream, &launches);
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
     h->last_launches = launches;
     if (octave == h->octaves - 1 && level == h->nl - 1) {
@@ -625,6 +638,9 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "bx")) h->tune.bx = value;
     else if (!std::strcmp(key, "pdl")) h->tune.pdl = value;
     else if (!std::strcmp(key, "timing")) h->tune.timing = value;
+    else if (!std::strcmp(key, "conv_tall")) h->tune.conv_tall = value;
+    else if (!std::strcmp(key, "conv_streams")) h->tune.conv_streams = value;
+    else if (!std::strcmp(key, "conv_pipe")) h->tune.conv_pipe = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
     return SSPYR_OK;
 }

@@ -50,6 +50,9 @@ struct Tuning {
     int block = 0;             // threads per CTA
     int bx = 0;                // CTA width in quads (threads along a row); 0 = pick the least-padding width
     int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
+    int conv_tall = 0;         // CONV: 64-row tiles (radii <= 6)
+    int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
+    int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
                                // launches stop them from overlapping, so this is off unless asked for
 };
@@ -86,6 +89,8 @@ struct sspyr_ctx {
     unsigned char* d_halo_raw = nullptr;     // same for the raw frame (octave 0, level 0): [up|down][rmax][in_pitch]
     int halo_rmax = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::vector<cudaStream_t> aux;           // CONV: one extra stream per octave >= 1
+    std::vector<cudaEvent_t> ev_base, ev_done;
     bool timed = false;
     int last_launches = 0;
     int last_first = 0, last_count = 0;      // frame slots the previous kernel wrote (PDL overlap guard)
@@ -98,7 +103,8 @@ namespace sspyr {
 // Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
 cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
 cudaError_t launch_conv(const sspyr_ctx* h, int first_frame, int count, int* launches);
-cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, int* launches);
+cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,
+                             int* launches);
 bool conv_has_up(const sspyr_ctx* h);
 bool conv_has_down(const sspyr_ctx* h);
 float* conv_halo_plane(const sspyr_ctx* h, int octave, int down);
