@@ -241,7 +241,7 @@ def run_native(args) -> dict:
                             band_row0=row0, full_height=full_h)
         ss.set_stream(stream.cuda_stream)
         if args.tune:
-            ss.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(","))})
+            ss.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)})
         for s in range(slots):   # distinct synthetic frames, resident in HBM before the timed region
             ss.upload(pkg.synth.noise(rows, width, frame=rank * 1000 + s, row0=row0), frame=s)
         ss.sync()

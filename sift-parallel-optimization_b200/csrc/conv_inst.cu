@@ -1,7 +1,7 @@
 // csrc/conv_inst.cu -- one translation unit per tap radius (compiled with -DSSPYR_R=<radius>, in parallel):
 // instantiates the fused CONV level kernel of conv_kernel.cuh for every input kind.  SSPYR_R == 0 builds the
 // radius-independent extremum scan instead.
-#include "conv_kernel.cuh"
+#include "conv_march.cuh"
 
 #ifndef SSPYR_R
 #error "compile with -DSSPYR_R=<radius>"
@@ -23,5 +23,11 @@ cudaError_t SSPYR_CAT(launch_conv_r, SSPYR_R)(const ConvParams& P, int src_kind,
                                               int frames, int sms) {
     return launch_conv_src<SSPYR_R>(P, src_kind, variant, st, device, frames, sms);
 }
+#if SSPYR_R <= 12
+cudaError_t SSPYR_CAT(launch_march_r, SSPYR_R)(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
+                                               int sms) {
+    return launch_march_src<SSPYR_R>(P, src_kind, st, device, frames, sms);
+}
+#endif
 #endif
 }  // namespace sspyr

@@ -11,6 +11,10 @@ SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_DECL(14) SSPYR_DECL(15) SSPYR_DECL(16)
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 #undef SSPYR_DECL
+#define SSPYR_DECL(n) cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int);
+SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
+SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
+#undef SSPYR_DECL
 cudaError_t launch_extrema_octave(const float*, unsigned char*, int, int, int, int, unsigned long long, float, cudaStream_t);
 
 namespace {
@@ -24,6 +28,16 @@ cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cud
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12) SSPYR_CASE(13) SSPYR_CASE(14) SSPYR_CASE(15)
         SSPYR_CASE(16) SSPYR_CASE(20) SSPYR_CASE(24) SSPYR_CASE(28) SSPYR_CASE(32)
+#undef SSPYR_CASE
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms) {
+    switch (r) {
+#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms);
+        SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
+        SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
 #undef SSPYR_CASE
         default: return cudaErrorInvalidValue;
     }
@@ -89,7 +103,12 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     const int variant = (h->tune.conv_tall > 0 ? 1 : 0) | (h->tune.conv_pipe > 0 ? 2 : 0);   // default: 32-row, one tile per CTA
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    const cudaError_t e = dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
+    // Large levels (enough 512-column strips x 32-row segments to fill the GPU in one wave) march down column
+    // strips with the column pass in registers; small ones use the shared-memory tile kernel.
+    const long long march_ctas = (long long)((g.W + 511) / 512) * ((g.H + 31) / 32) * count;
+    const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && march_ctas >= 2LL * sms));
+    const cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms)
+                                : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     return e;
 }

@@ -52,6 +52,7 @@ struct Tuning {
     int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
     int conv_tall = 0;         // CONV: 64-row tiles (radii <= 6)
     int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
+    int conv_march = 0;        // CONV: column-strip marching kernel (R <= 12): 1 on, -1 by level size; measured slower (profiles/)
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
                                // launches stop them from overlapping, so this is off unless asked for

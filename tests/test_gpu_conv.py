@@ -146,3 +146,43 @@ def test_extrema_flags(pkg, O, synth):
                 total += int(want.sum())
             if mode == pkg.MODE_CONV:
                 assert total > 0
+
+
+@pytest.mark.parametrize("h,w,octs,S,rs", [(270, 480, 4, 3, 3.0), (135, 1241, 3, 3, 3.0), (600, 700, 3, 3, 4.0),
+                                           (97, 513, 2, 2, 3.0), (64, 2100, 2, 3, 3.0)])
+def test_marching_kernel_equals_tile_kernel(pkg, O, synth, h, w, octs, S, rs):
+    """The column-strip marching kernel (large levels) does the same FMA chains in the same order as the
+    shared-memory tile kernel: bit-identical results, and both within tolerance of the specification."""
+    img = synth.noise(h, w)
+    out = {}
+    for march in (0, 1):
+        with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=2) as ss:
+            ss.set_tuning(conv_march=march)
+            ss.upload(img, frame=0)
+            ss.upload(synth.noise(h, w, frame=5), frame=1)
+            ss.build_batch(0, 2)
+            out[march] = (ss.download_gauss(0), ss.download_dog(0), ss.download_gauss(1))
+    for a, b in zip(out[0], out[1]):
+        for o in range(octs):
+            np.testing.assert_array_equal(a[o], b[o])
+    ref = O.conv_build(img, octs, S, radius_sigmas=rs)
+    check(out[1][0], ref["gauss"], 255.0, "march gauss")
+    check(out[1][1], ref["dog"], 255.0, "march dog")
+
+
+def test_marching_kernel_on_row_bands(pkg, O, synth):
+    h, w, octs, S = 512, 640, 3, 3
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, S)
+    hs = []
+    for r in range(2):
+        row0, rows = pkg.band_rows(h, octs, 2, r)
+        b = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, band_row0=row0, full_height=h)
+        b.set_tuning(conv_march=1)
+        b.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+        hs.append((row0, rows, b))
+    pkg.LocalExchanger([b for _, _, b in hs]).build()
+    for row0, rows, b in hs:
+        want = [ref["gauss"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)]
+        check(b.download_gauss(), want, 255.0, f"band@{row0}")
+        b.close()
