@@ -1,0 +1,65 @@
+"""scripts/check_conv_bands_nccl.py -- run under torchrun on N GPUs: CONV-mode row bands with the per-level NCCL
+halo exchange (exchange.DistExchanger) must reproduce the specification (oracle) on every rank's band, and the
+REF-mode bands (no exchange) must be bit-exact.  Prints one PASS/FAIL line per rank.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        scripts/check_conv_bands_nccl.py
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def main() -> int:
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    pkg, O = entry.load_package(), entry.load_oracle()
+    h, w, octs, S = 1088, 1500, 4, 3
+    img = pkg.synth.noise(h, w, frame=11)
+    row0, rows = pkg.band_rows(h, octs, world, rank)
+    ok = True
+    # CONV: halo exchange over NCCL P2P before every level
+    ref = O.conv_build(img, octs, S)
+    ss = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, device=local, band_row0=row0, full_height=h)
+    ss.set_stream(torch.cuda.current_stream().cuda_stream)
+    ss.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+    ex = pkg.DistExchanger(ss, rank, world, dev)
+    ex.build()
+    ex.build()                                   # twice: the schedule must be re-entrant
+    worst = 0.0
+    for kind, got in (("gauss", ss.download_gauss()), ("dog", ss.download_dog())):
+        for o in range(octs):
+            want = ref[kind][o][:, row0 >> o:(row0 >> o) + (rows >> o)]
+            err = float(np.max(np.abs(got[o].astype(np.float64) - want)))
+            worst = max(worst, err)
+            ok &= err <= 1e-4 * 255
+    ss.close()
+    # REF: no exchange at all, bit-exact
+    rref = O.ref_build(img, octaves=octs, S=S, want=("inplace",))["inplace"]
+    with pkg.ScaleSpace(rows, w, octs, S, device=local, band_row0=row0, full_height=h) as rs:
+        rs.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+        rs.build()
+        for o, a in enumerate(rs.download_inplace()):
+            want = rref[o][:, row0 >> o:(row0 >> o) + (rows >> o)]
+            ok &= bool(np.array_equal(a.view(np.uint32), np.ascontiguousarray(want).view(np.uint32)))
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    print(f"rank {rank}/{world} band rows [{row0},{row0 + rows}) CONV max|err|={worst:.3g} "
+          f"{'PASS' if ok else 'FAIL'} (all ranks: {'PASS' if int(flag.item()) else 'FAIL'})", flush=True)
+    dist.destroy_process_group()
+    return 0 if int(flag.item()) else 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -43,6 +43,36 @@ __global__ void read1_write_planes(const float4* __restrict__ in, float4* __rest
     for (int p = 0; p < planes; ++p) { __stcs(out + p * plane_vec + i, v); v.x += 1.f; }
 }
 
+__global__ void read1_write_planes_pdl(const float4* __restrict__ in, float4* __restrict__ out, size_t plane_vec, int planes, size_t n_vec) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_vec) {
+        float4 v = in[i];
+        for (int p = 0; p < planes; ++p) { __stcs(out + p * plane_vec + i, v); v.x += 1.f; }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// same, and every CTA first pulls a slice of the NEXT frame's input into L2 (prefetch.global.L2)
+__global__ void read1_write_planes_pdl_pf(const float4* __restrict__ in, const float4* __restrict__ next_in, float4* __restrict__ out,
+                                          size_t plane_vec, int planes, size_t n_vec) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_vec) {
+        if ((threadIdx.x & 7) == 0) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(next_in + i));
+        float4 v = in[i];
+        for (int p = 0; p < planes; ++p) { __stcs(out + p * plane_vec + i, v); v.x += 1.f; }
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// bulk L2 prefetch of one plane by a small grid (one 128-byte line per thread)
+__global__ void l2_prefetch(const char* __restrict__ p, size_t bytes) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128;
+    if (i < bytes) asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(p + i));
+}
+
 int main(int argc, char** argv) {
     const size_t px_list[] = {2073600 * 4 / 3, 8294400 * 4 / 3, 33177600 * 4 / 3};   // ~ sum over octaves of c2, c3, c4 pixels
     const char* names[] = {"c2-like", "c3-like", "c4-like"};
@@ -77,6 +107,26 @@ int main(int argc, char** argv) {
             cfg.attrs = a; cfg.numAttrs = 1;
             CK(cudaLaunchKernelEx(&cfg, write_planes_pdl, out + (size_t)s * n_vec * planes, n_vec, planes, n_vec)); }, (double)frame_bytes);
         time_it("read 1 + write 11 planes, st.cs", [&](int s) { read1_write_planes<<<grid, block, 0, st>>>(in + (size_t)s * n_vec, out + (size_t)s * n_vec * planes, n_vec, planes, n_vec); }, (double)frame_bytes + px * 4.0);
+        auto pdl_cfg = [&](cudaLaunchConfig_t& cfg, cudaLaunchAttribute* a, unsigned g) {
+            cfg = cudaLaunchConfig_t{}; cfg.gridDim = dim3(g); cfg.blockDim = dim3(block); cfg.stream = st;
+            a[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; a[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = a; cfg.numAttrs = 1; };
+        time_it("read 1 + write 11, PDL", [&](int s) {
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute a[1]; pdl_cfg(cfg, a, grid);
+            CK(cudaLaunchKernelEx(&cfg, read1_write_planes_pdl, (const float4*)(in + (size_t)s * n_vec), out + (size_t)s * n_vec * planes, n_vec, planes, n_vec)); }, (double)frame_bytes + px * 4.0);
+        time_it("read 1 (L2-resident) + write 11, PDL", [&](int s) {
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute a[1]; pdl_cfg(cfg, a, grid);
+            CK(cudaLaunchKernelEx(&cfg, read1_write_planes_pdl, (const float4*)in, out + (size_t)s * n_vec * planes, n_vec, planes, n_vec)); }, (double)frame_bytes + px * 4.0);
+        time_it("read 1 + write 11, PDL, in-kernel L2 prefetch of next", [&](int s) {
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute a[1]; pdl_cfg(cfg, a, grid);
+            CK(cudaLaunchKernelEx(&cfg, read1_write_planes_pdl_pf, (const float4*)(in + (size_t)s * n_vec), (const float4*)(in + (size_t)((s + 1) % slots) * n_vec),
+                                  out + (size_t)s * n_vec * planes, n_vec, planes, n_vec)); }, (double)frame_bytes + px * 4.0);
+        time_it("read 1 + write 11, PDL, separate L2 prefetch kernel", [&](int s) {
+            cudaLaunchConfig_t cfg; cudaLaunchAttribute a[1];
+            const size_t bytes = px * 4; pdl_cfg(cfg, a, (unsigned)((bytes / 128 + block - 1) / block));
+            CK(cudaLaunchKernelEx(&cfg, l2_prefetch, (const char*)(in + (size_t)((s + 1) % slots) * n_vec), bytes));
+            pdl_cfg(cfg, a, grid);
+            CK(cudaLaunchKernelEx(&cfg, read1_write_planes_pdl, (const float4*)(in + (size_t)s * n_vec), out + (size_t)s * n_vec * planes, n_vec, planes, n_vec)); }, (double)frame_bytes + px * 4.0);
         time_it("write 1 plane x11 launches-equivalent", [&](int s) { write_planes<true><<<grid, block, 0, st>>>(out + (size_t)s * n_vec * planes, n_vec, 1, n_vec); }, (double)px * 4);
         const size_t cp_vec = frame_bytes / 2 / 16;
         const unsigned cgrid = (unsigned)((cp_vec + block - 1) / block);
