@@ -32,8 +32,8 @@ def run(name, outputs, tunings, steps):
         ss.upload(pkg.synth.noise(h, w, frame=s), frame=s)
     ss.sync()
     rows = []
-    for rpt, block, bx, pdl in tunings:
-        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl)
+    for rpt, block, bx, pdl, occ in tunings:
+        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl, occ=occ)
         for i in range(20):
             ss.build(i % slots)
         torch.cuda.synchronize()
@@ -45,19 +45,19 @@ def run(name, outputs, tunings, steps):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) / steps * 1e3
         gbs = fb / us / 1e3
-        rows.append((us, rpt, block, bx, pdl, gbs))
-        print(f"{name} out={outputs} rpt={rpt} block={block} bx={bx} pdl={pdl}: {us:8.2f} us/frame  {gbs:7.1f} GB/s  "
+        rows.append((us, rpt, block, bx, pdl, occ, gbs))
+        print(f"{name} out={outputs} rpt={rpt} block={block} bx={bx} pdl={pdl} occ={occ}: {us:8.2f} us/frame  {gbs:7.1f} GB/s  "
               f"frac={gbs / PEAK:.3f}  {h * w / us:9.1f} Mpix/s", flush=True)
     ss.close()
     best = min(rows)
-    print(f"BEST {name} out={outputs}: rpt={best[1]} block={best[2]} bx={best[3]} pdl={best[4]} -> {best[0]:.2f} us, "
-          f"{best[5]:.1f} GB/s, frac={best[5] / PEAK:.3f}", flush=True)
+    print(f"BEST {name} out={outputs}: rpt={best[1]} block={best[2]} bx={best[3]} pdl={best[4]} occ={best[5]} -> {best[0]:.2f} us, "
+          f"{best[6]:.1f} GB/s, frac={best[6] / PEAK:.3f}", flush=True)
 
 
 if __name__ == "__main__":
     names = sys.argv[1:] or ["c2", "c3"]
-    tunings = list(itertools.product((1, 2, 4), (128, 256), (0, 32), (1, 0)))
+    tunings = list(itertools.product((1, 2), (96, 128), (0, 32), (1,), (0, 2, 3, 4, 5, 6, 8, 12)))
     for name in names:
         steps = {"c1": 2000, "c2": 1000, "c3": 300, "c4": 100}[name]
         run(name, pkg.OUT_ALL, tunings, steps)
-    run("c2", pkg.OUT_INPLACE, [(1, 256, 0, 1), (2, 256, 0, 1), (4, 256, 0, 1), (2, 256, 0, 0)], 1000)
+    run("c2", pkg.OUT_INPLACE, [(1, 128, 0, 1, 0), (2, 128, 0, 1, 0), (1, 128, 0, 1, 4), (2, 128, 0, 1, 4)], 1000)

@@ -18,7 +18,9 @@
 //     level is ever materialised before its final value (the reference writes every level 3 times).
 //   * Every load a thread needs (pixel quads of its RPT rows, column windows, row windows) is issued
 //     BEFORE its first store, so a thread pays one DRAM latency, not one per level (stores may alias the
-//     tables as far as the compiler knows, so it cannot hoist them itself).
+//     tables as far as the compiler knows, so it cannot hoist them itself).  Threads are persistent down the
+//     frame: column windows are loaded once and the next row group is prefetched before the current one is
+//     stored, so the store stream never stalls behind a DRAM read.
 //   * 128-bit coalesced loads (ld.global.nc) and streaming stores (st.global.cs): a warp writes 512
 //     contiguous bytes per plane per row; rows are 128-byte aligned (pitch % 32 == 0).  Row windows are
 //     stored transposed, [row][8], so one row's S+3 values are two warp-uniform 128-bit loads.
@@ -158,90 +160,115 @@ __device__ __forceinline__ void load_quad(float (&p)[4], const unsigned char* __
 template <int PIX> __host__ __device__ constexpr int elem_bytes() { return PIX == SSPYR_PIXEL_U8 ? 1 : 4; }
 
 // grid.x: blocks of BX quads along a row;  grid.y: blocks of BY row groups (RPT rows each);  grid.z: frame.
+// Everything one thread needs for RPT consecutive rows of its column quad.
+template <int NL, int RPT>
+struct RefRows {
+    float p[RPT][4];                 // pixel quads (K0's int->float cast already applied)
+    float f0[RPT][NL];               // octave-0 row windows
+    float f1[(RPT + 1) / 2][NL];     // octave-1 row windows of the even rows
+};
+
 template <int NL, int PIX, int RPT>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void ref_load_rows(RefRows<NL, RPT>& q, const RefParams& P, const unsigned char* __restrict__ img,
+                                              int r0, int c, bool col1) {
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) {
+        const int r = min(r0 + rr, P.H - 1);                        // clamp: rows past the end are not stored
+        load_quad<PIX>(q.p[rr], img + (size_t)r * P.img_pitch * elem_bytes<PIX>(), c, P.W);
+    }
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) load_row_window<NL>(q.f0[rr], P.oct[0].fh, min(r0 + rr, P.H - 1));
+    if (col1 && (RPT > 1 || (r0 & 1) == 0)) {
+#pragma unroll
+        for (int k = 0; k < (RPT + 1) / 2; ++k) load_row_window<NL>(q.f1[k], P.oct[1].fh, min((r0 >> 1) + k, P.oct[1].H - 1));
+    }
+}
+
+// grid.x: blocks of bx quads along a row;  grid.y: blocks of by row groups (RPT rows each);  grid.z: frame.
+// A thread keeps its column quad and walks down the frame in steps of gridDim.y*blockDim.y*RPT rows: the column
+// windows are loaded once, and the loads of the NEXT row group are issued before the stores of the current one
+// (software prefetch), so after the first group no thread ever waits on DRAM with its stores unissued.  With a
+// grid that covers every row group the loop runs once.
+template <int NL, int PIX, int RPT>
+__global__ void __launch_bounds__(128, 4)
 ref_fused_kernel(const __grid_constant__ RefParams P) {
     // Frames are independent: let the next launch in the stream start filling SMs right away (PDL).
     asm volatile("griddepcontrol.launch_dependents;");
 
     const int j = blockIdx.x * blockDim.x + threadIdx.x;            // quad index along the row
-    const int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * RPT;   // first of this thread's RPT rows
+    int r0 = (blockIdx.y * blockDim.y + threadIdx.y) * RPT;         // first of this thread's RPT rows
+    const int stride = gridDim.y * blockDim.y * RPT;
     const int c = j << 2;
-    if (c >= P.W || r0 >= P.H) return;
-    const unsigned char* __restrict__ img =
-        static_cast<const unsigned char*>(P.img) + (size_t)blockIdx.z * P.img_frame_stride;
-    const size_t fofs = (size_t)blockIdx.z * P.out_frame_stride;
-    const int outputs = P.outputs;
+    if (c < P.W && r0 < P.H) {
+        const unsigned char* __restrict__ img =
+            static_cast<const unsigned char*>(P.img) + (size_t)blockIdx.z * P.img_frame_stride;
+        const size_t fofs = (size_t)blockIdx.z * P.out_frame_stride;
+        const int outputs = P.outputs;
+        const RefOct& o0 = P.oct[0];
+        const RefOct& o1 = P.oct[1];
+        const int ocol1 = c >> 1;
+        const bool col1 = P.octaves > 1 && ocol1 < o1.W;            // this quad feeds octave 1 (input columns c, c+2)
+        constexpr int R1 = (RPT + 1) / 2;
 
-    // ---- issue every load first -------------------------------------------------------------------
-    float p[RPT][4];
-#pragma unroll
-    for (int rr = 0; rr < RPT; ++rr) {
-        const int r = min(r0 + rr, P.H - 1);                        // clamp: rows past the end are not stored
-        load_quad<PIX>(p[rr], img + (size_t)r * P.img_pitch * elem_bytes<PIX>(), c, P.W);
-    }
-    const RefOct& o0 = P.oct[0];
-    float w0[NL][4];
-    load_windows<NL, 4>(w0, o0.fw, o0.pitch, c);
-    float f0[RPT][NL];
-#pragma unroll
-    for (int rr = 0; rr < RPT; ++rr) load_row_window<NL>(f0[rr], o0.fh, min(r0 + rr, P.H - 1));
+        // ---- loads that do not depend on the row: column windows of octaves 0 and 1 ----------------------
+        float w0[NL][4];
+        load_windows<NL, 4>(w0, o0.fw, o0.pitch, c);
+        float w1[NL][2];
+        if (col1) load_windows<NL, 2>(w1, o1.fw, o1.pitch, ocol1);
+        RefRows<NL, RPT> cur;
+        ref_load_rows<NL, PIX, RPT>(cur, P, img, r0, c, col1);
+        const int nvalid0 = o0.W - c, nvalid1 = o1.W - ocol1;
 
-    // octave 1 is fed by the even rows of this thread (r0 is a multiple of RPT): input columns c, c+2
-    constexpr int R1 = (RPT + 1) / 2;
-    const bool even0 = (RPT > 1) || ((r0 & 1) == 0);
-    const RefOct& o1 = P.oct[1];
-    const int ocol1 = c >> 1;
-    const bool has1 = P.octaves > 1 && even0 && ocol1 < o1.W;
-    float w1[NL][2];
-    float f1[R1][NL];
-    if (has1) {
-        load_windows<NL, 2>(w1, o1.fw, o1.pitch, ocol1);
-#pragma unroll
-        for (int k = 0; k < R1; ++k) load_row_window<NL>(f1[k], o1.fh, min((r0 >> 1) + k, o1.H - 1));
-    }
+        for (;;) {
+            const int rn = r0 + stride;
+            const bool more = rn < P.H;
+            RefRows<NL, RPT> nxt;
+            if (more) ref_load_rows<NL, PIX, RPT>(nxt, P, img, rn, c, col1);   // prefetch before this group's stores
 
-    // ---- octave 0 -----------------------------------------------------------------------------------
-    float* out0 = o0.base + fofs + (size_t)r0 * o0.pitch + c;
-    const int nvalid0 = o0.W - c;
+            // ---- octave 0 ----------------------------------------------------------------------------------
+            float* out0 = o0.base + fofs + (size_t)r0 * o0.pitch + c;
 #pragma unroll
-    for (int rr = 0; rr < RPT; ++rr)
-        if (r0 + rr < P.H)
-            emit_dispatch<NL, 4>(out0 + (size_t)rr * o0.pitch, (unsigned)o0.plane, outputs, nvalid0, p[rr], w0, f0[rr]);
+            for (int rr = 0; rr < RPT; ++rr)
+                if (r0 + rr < P.H)
+                    emit_dispatch<NL, 4>(out0 + (size_t)rr * o0.pitch, (unsigned)o0.plane, outputs, nvalid0, cur.p[rr], w0, cur.f0[rr]);
 
-    // ---- octave 1 -----------------------------------------------------------------------------------
-    if (has1) {
-        float* out1 = o1.base + fofs + (size_t)(r0 >> 1) * o1.pitch + ocol1;
-        const int nvalid1 = o1.W - ocol1;
+            // ---- octave 1: even rows of the group (r0 is a multiple of RPT) ------------------------------------
+            if (col1 && (RPT > 1 || (r0 & 1) == 0)) {
+                float* out1 = o1.base + fofs + (size_t)(r0 >> 1) * o1.pitch + ocol1;
 #pragma unroll
-        for (int k = 0; k < R1; ++k) {
-            const int orow = (r0 >> 1) + k;
-            if (orow < o1.H && r0 + 2 * k < P.H) {
-                const float p2[2] = {p[2 * k < RPT ? 2 * k : 0][0], p[2 * k < RPT ? 2 * k : 0][2]};
-                emit_dispatch<NL, 2>(out1 + (size_t)k * o1.pitch, (unsigned)o1.plane, outputs, nvalid1, p2, w1, f1[k]);
+                for (int k = 0; k < R1; ++k) {
+                    const int orow = (r0 >> 1) + k;
+                    if (orow < o1.H && r0 + 2 * k < P.H) {
+                        const float p2[2] = {cur.p[2 * k < RPT ? 2 * k : 0][0], cur.p[2 * k < RPT ? 2 * k : 0][2]};
+                        emit_dispatch<NL, 2>(out1 + (size_t)k * o1.pitch, (unsigned)o1.plane, outputs, nvalid1, p2, w1, cur.f1[k]);
+                    }
+                }
             }
-        }
-    }
 
-    // ---- octaves >= 2: one pixel per participating quad (1/16 of the octave-0 work and falling) -------
+            // ---- octaves >= 2: one pixel per participating quad (1/16 of the octave-0 work and falling) ------
 #pragma unroll
-    for (int rr = 0; rr < RPT; rr += 4) {
-        const int r = r0 + rr;
-        if (r >= P.H) break;
-        for (int o = 2; o < P.octaves; ++o) {
-            if ((r & ((1 << o) - 1)) != 0) break;
-            if ((j & ((1 << (o - 2)) - 1)) != 0) break;             // column 4j must be a multiple of 2^o
-            const RefOct& oc = P.oct[o];
-            const int orow = r >> o, ocol = c >> o;
-            if (orow < oc.H && ocol < oc.W) {
-                const float p1[1] = {p[rr][0]};
-                float wv[NL][1];
-                float fv[NL];
-                load_windows<NL, 1>(wv, oc.fw, oc.pitch, ocol);
-                load_row_window<NL>(fv, oc.fh, orow);
-                emit_levels<NL, 1, true>(oc.base + fofs + (size_t)orow * oc.pitch + ocol, (unsigned)oc.plane, outputs,
-                                         1, p1, wv, fv);
+            for (int rr = 0; rr < RPT; rr += 4) {
+                const int r = r0 + rr;
+                if (r >= P.H) break;
+                for (int o = 2; o < P.octaves; ++o) {
+                    if ((r & ((1 << o) - 1)) != 0) break;
+                    if ((j & ((1 << (o - 2)) - 1)) != 0) break;     // column 4j must be a multiple of 2^o
+                    const RefOct& oc = P.oct[o];
+                    const int orow = r >> o, ocol = c >> o;
+                    if (orow < oc.H && ocol < oc.W) {
+                        const float p1[1] = {cur.p[rr][0]};
+                        float wv[NL][1];
+                        float fv[NL];
+                        load_windows<NL, 1>(wv, oc.fw, oc.pitch, ocol);
+                        load_row_window<NL>(fv, oc.fh, orow);
+                        emit_levels<NL, 1, true>(oc.base + fofs + (size_t)orow * oc.pitch + ocol, (unsigned)oc.plane, outputs,
+                                                 1, p1, wv, fv);
+                    }
+                }
             }
+            if (!more) break;
+            cur = nxt;
+            r0 = rn;
         }
     }
     // Chain completion: this grid may not finish before the grid it overlapped with has finished and
@@ -268,8 +295,7 @@ template <int NL, int PIX>
 cudaError_t launch_rpt(const RefParams& P, int rpt, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     switch (rpt) {
         case 1: return launch_one<NL, PIX, 1>(P, grid, block, st, pdl);
-        case 2: return launch_one<NL, PIX, 2>(P, grid, block, st, pdl);
-        default: return launch_one<NL, PIX, 4>(P, grid, block, st, pdl);
+        default: return launch_one<NL, PIX, 2>(P, grid, block, st, pdl);
     }
 }
 

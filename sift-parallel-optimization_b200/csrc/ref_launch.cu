@@ -55,9 +55,9 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
 
         int rpt = h->tune.rows_per_thread;
         if (rpt <= 0) rpt = 2;                       // measured best on C2..C4 (profiles/, sweep_ref.py)
-        rpt = rpt >= 4 ? 4 : rpt >= 2 ? 2 : 1;
+        rpt = rpt >= 2 ? 2 : 1;
         int threads = h->tune.block > 0 ? h->tune.block : 128;
-        threads = threads > 256 ? 256 : (threads < 32 ? 32 : (threads / 32) * 32);
+        threads = threads > 128 ? 128 : (threads < 32 ? 32 : (threads / 32) * 32);   // kernels are built for <= 128
         const int W4 = (P.W + 3) >> 2;
         int bx = h->tune.bx;
         if (bx <= 0) {   // widest CTA row among {128,96,64,32} that wastes the fewest padded quads
@@ -72,7 +72,16 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
         const int by = threads / bx > 0 ? threads / bx : 1;
         const int row_groups = (P.H + rpt - 1) / rpt;
         const dim3 block(bx, by, 1);
-        const dim3 grid((W4 + bx - 1) / bx, (row_groups + by - 1) / by, n);
+        int gy = (row_groups + by - 1) / by;
+        // persistent rows: cap the grid at `occ` CTAs per SM so that every thread walks several row groups and
+        // prefetches the next one while it stores the current one
+        if (h->tune.occ > 0) {
+            const long long gx = (W4 + bx - 1) / bx;
+            long long cap = ((long long)sm_count(h->device) * h->tune.occ + gx * n - 1) / (gx * n);
+            if (cap < 1) cap = 1;
+            if (gy > cap) gy = (int)cap;
+        }
+        const dim3 grid((W4 + bx - 1) / bx, gy, n);
         // Overlap with the previous launch only when it wrote other frame slots: two builds of the SAME slot
         // (e.g. a K0-only stage followed by the full build) must stay ordered or their stores would race.
         bool clash = false;

@@ -49,6 +49,7 @@ struct Tuning {
     int rows_per_thread = 0;   // 0 = default
     int block = 0;             // threads per CTA
     int bx = 0;                // CTA width in quads (threads along a row); 0 = pick the least-padding width
+    int occ = 0;               // REF: > 0 = persistent grid of this many CTAs per SM (row-group prefetch); 0 = one group per thread
     int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
     int conv_tall = 0;         // CONV: 64-row tiles (radii <= 6)
     int conv_pipe = 0;         // CONV: persistent double-buffered CTAs

@@ -208,14 +208,14 @@ def test_device_resident_input_via_torch(pkg, O, synth):
             ss.set_input_device(t.data_ptr() + 4, 0)                         # misaligned
 
 
-@pytest.mark.parametrize("rpt,block,bx,pdl", [(1, 128, 0, 1), (2, 256, 32, 1), (4, 64, 64, 0), (4, 256, 128, 1),
-                                              (1, 256, 96, 0), (2, 96, 96, 1)])
-def test_every_tuning_is_bit_exact(pkg, O, synth, rpt, block, bx, pdl):
+@pytest.mark.parametrize("rpt,block,bx,pdl,occ", [(1, 128, 0, 1, 0), (2, 256, 32, 1, 0), (4, 64, 64, 0, 1), (4, 256, 128, 1, 3),
+                                                  (1, 256, 96, 0, 2), (2, 96, 96, 1, 5), (1, 32, 32, 1, 1)])
+def test_every_tuning_is_bit_exact(pkg, O, synth, rpt, block, bx, pdl, occ):
     h, w = 203, 330
     img = synth.noise(h, w)
     ref = O.ref_build(img, octaves=5, S=3)
     with pkg.ScaleSpace(h, w, 5, 3) as ss:
-        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl)
+        ss.set_tuning(rows_per_thread=rpt, block=block, bx=bx, pdl=pdl, occ=occ)
         ss.upload(img)
         ss.build()
         for o, a in enumerate(ss.download_gauss()):
