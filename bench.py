@@ -60,6 +60,8 @@ def parse_args():
     ap.add_argument("--outputs", default="all", choices=["all", "inplace"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="CONV row bands: read neighbour planes in the kernel over NVLink (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--tune", default="", help="rows_per_thread=2,block=256,bx=0,pdl=1")
     return ap.parse_args()
 
@@ -250,7 +252,8 @@ def run_native(args) -> dict:
     cursor = [0]
     exchanger = None
     if ss is not None and args.mode == "conv" and part == "rowband" and world > 1:
-        exchanger = pkg.DistExchanger(ss, rank, world, torch.device("cuda", local))
+        exchanger = (pkg.PeerExchanger(ss, rank, world) if args.halo == "peer"
+                     else pkg.DistExchanger(ss, rank, world, torch.device("cuda", local)))
 
     def step():
         """One pass over this rank's share of the batch: my_frames frames through the slot ring."""
@@ -258,7 +261,7 @@ def run_native(args) -> dict:
             return
         if exchanger is not None:            # CONV row bands: per-level neighbour halo exchange over NCCL P2P
             exchanger.build(cursor[0])
-            launches[0] += conv_launches
+            launches[0] += conv_launches if args.halo == "nccl" else ss.last_launches()
             cursor[0] = (cursor[0] + 1) % slots
             return
         left = my_frames

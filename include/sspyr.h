@@ -193,6 +193,20 @@ SSPYR_API int sspyr_halo_ptrs(sspyr_handle h, int frame, int octave, int level, 
  * runs the blur that PRODUCES (octave, level). */
 SSPYR_API int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level);
 
+/* ---- row-band CONV over NVLink peer memory: halo rows are read inside the blur kernel ------------------- */
+/* Instead of exchanging halo rows into staging buffers (sspyr_halo_ptrs), a band can ATTACH its neighbours:
+ * the level kernels then load the rows they need straight from the neighbour's planes over NVLink, and tiny
+ * signal / wait kernels on a progress counter in peer memory keep the bands in step.  One process per GPU:
+ * export a blob here, ship it to the neighbours (any host transport), attach it there (CUDA IPC).  Bands of one
+ * process attach each other's handles directly.  Every band must issue the same sspyr_conv_step sequence;
+ * inputs must be uploaded (and the ranks synchronised) before the first step of a frame. */
+#define SSPYR_IPC_BLOB_BYTES 1024
+#define SSPYR_SIDE_ABOVE 0
+#define SSPYR_SIDE_BELOW 1
+SSPYR_API int sspyr_ipc_export(sspyr_handle h, void* blob, size_t capacity, size_t* bytes);
+SSPYR_API int sspyr_ipc_attach(sspyr_handle h, int side, const void* blob, size_t bytes);
+SSPYR_API int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle neighbour);
+
 #ifdef __cplusplus
 }
 #endif

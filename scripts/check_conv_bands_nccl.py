@@ -45,6 +45,26 @@ def main() -> int:
             worst = max(worst, err)
             ok &= err <= 1e-4 * 255
     ss.close()
+    # CONV again with peer-memory halos: neighbours' planes mapped through CUDA IPC, read inside the blur kernel
+    ps = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, device=local, band_row0=row0, full_height=h)
+    ps.set_stream(torch.cuda.current_stream().cuda_stream)
+    ps.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+    ps.sync()
+    px = pkg.PeerExchanger(ps, rank, world)
+    px.build()
+    px.build_stepwise()
+    px.build()
+    ps.sync()
+    worst_peer = 0.0
+    for kind, got in (("gauss", ps.download_gauss()), ("dog", ps.download_dog())):
+        for o in range(octs):
+            want = ref[kind][o][:, row0 >> o:(row0 >> o) + (rows >> o)]
+            err = float(np.max(np.abs(got[o].astype(np.float64) - want)))
+            worst_peer = max(worst_peer, err)
+            ok &= err <= 1e-4 * 255
+    dist.barrier()
+    ps.close()
+    worst = max(worst, worst_peer)
     # REF: no exchange at all, bit-exact
     rref = O.ref_build(img, octaves=octs, S=S, want=("inplace",))["inplace"]
     with pkg.ScaleSpace(rows, w, octs, S, device=local, band_row0=row0, full_height=h) as rs:

@@ -9,9 +9,9 @@ from . import _lib, synth                                    # noqa: F401
 from ._lib import (KIND_DOG, KIND_EXTREMA, KIND_GAUSS, KIND_INPLACE, MODE_CONV, MODE_REF,    # noqa: F401
                    OUT_ALL, OUT_DOG, OUT_EXTREMA, OUT_GAUSS, OUT_GAUSS_TOP, OUT_INPLACE, PIXEL_F32,
                    PIXEL_I32, PIXEL_U8, STAGE_DOG, STAGE_FILTER, STAGE_INIT, SspyrError)
-from .exchange import DistExchanger, LocalExchanger          # noqa: F401
+from .exchange import DistExchanger, LocalExchanger, LocalPeerLink, PeerExchanger   # noqa: F401
 from .partition import band_rows, shard_frames               # noqa: F401
 from .pyramid import GaussPyramid, ScaleSpace                # noqa: F401
 
 __all__ = ["GaussPyramid", "ScaleSpace", "SspyrError", "synth", "band_rows", "shard_frames", "LocalExchanger",
-           "DistExchanger"]
+           "DistExchanger", "LocalPeerLink", "PeerExchanger"]

@@ -31,7 +31,10 @@ SYMBOLS = (
     "sspyr_build_batch", "sspyr_sync", "sspyr_elapsed_ms", "sspyr_last_launches", "sspyr_download",
     "sspyr_download_inplace", "sspyr_download_gauss", "sspyr_device_ptr", "sspyr_window_table",
     "sspyr_host_alloc", "sspyr_host_free", "sspyr_conv_taps", "sspyr_set_tuning", "sspyr_halo_rows", "sspyr_halo_ptrs", "sspyr_conv_step",
+    "sspyr_ipc_export", "sspyr_ipc_attach", "sspyr_peer_attach_local",
 )
+IPC_BLOB_BYTES = 1024
+SIDE_ABOVE, SIDE_BELOW = 0, 1
 
 
 class Config(C.Structure):
@@ -100,6 +103,9 @@ def load() -> C.CDLL:
         "sspyr_halo_ptrs": ([H, i, i, i, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp),
                              C.POINTER(sz)], i),
         "sspyr_conv_step": ([H, i, i, i], i),
+        "sspyr_ipc_export": ([H, vp, sz, C.POINTER(sz)], i),
+        "sspyr_ipc_attach": ([H, i, vp, sz], i),
+        "sspyr_peer_attach_local": ([H, i, H], i),
     }
     assert set(sig) == set(SYMBOLS)
     for name, (argtypes, restype) in sig.items():

@@ -19,6 +19,28 @@ cudaError_t launch_extrema_octave(const float*, unsigned char*, int, int, int, i
 
 namespace {
 
+// One thread publishes "this band has finished `value` level steps" to its neighbours (system-scope release:
+// everything the preceding kernels in the stream wrote is visible to a peer GPU that acquires the counter).
+__global__ void conv_signal_kernel(unsigned* flag, unsigned value) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+}
+
+// One thread waits until the neighbour's counter reaches `need`.  The neighbour runs on another GPU, so it
+// makes progress on its own; a bounded spin (about 2 s) marks flag[1] instead of hanging the device.
+__global__ void conv_wait_kernel(const unsigned* peer_flag, int count, unsigned need, unsigned* my_flags) {
+    const long long t0 = clock64();
+    for (int i = 0; i < count; ++i) {            // `count` consecutive counters must all have reached `need`
+        for (;;) {
+            unsigned v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peer_flag + i) : "memory");
+            if (v >= need) break;
+            if (clock64() - t0 > 4000000000LL) { my_flags[CONV_FLAG_TIMEOUT] = need; return; }
+            __nanosleep(200);
+        }
+    }
+}
+
 // compiled radius that serves a requested one (taps are zero-padded up to it)
 int compiled_radius(int r) { return r <= 16 ? r : r <= 20 ? 20 : r <= 24 ? 24 : r <= 28 ? 28 : 32; }
 
@@ -72,6 +94,10 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         src_kind = h->cfg.pixel_type;
         P.top_halo = conv_has_up(h) ? conv_halo_raw(h, 0) : nullptr;
         P.bot_halo = conv_has_down(h) ? conv_halo_raw(h, 1) : nullptr;
+        const int R0 = h->conv[0].radius;
+        if (h->peer[0].attached)      // last R rows of the band above / first rows of the band below, in place
+            P.top_halo = h->peer[0].in + (size_t)first * h->peer[0].in_frame_bytes + (size_t)(h->peer[0].height - R0) * h->in_pitch_bytes;
+        if (h->peer[1].attached) P.bot_halo = h->peer[1].in + (size_t)first * h->peer[1].in_frame_bytes;
     } else {
         P.src = frame_out(h, first) + g.off + (size_t)plane_index(nl, SSPYR_KIND_GAUSS, level - 1) * g.plane;
         P.src_pitch = g.pitch;
@@ -79,6 +105,15 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         src_kind = CONV_SRC_PLANE;
         P.top_halo = conv_has_up(h) ? conv_halo_plane(h, octave, 0) : nullptr;
         P.bot_halo = conv_has_down(h) ? conv_halo_plane(h, octave, 1) : nullptr;
+        const int Rl = h->conv[level].radius;
+        const int pi = plane_index(nl, SSPYR_KIND_GAUSS, level - 1);
+        for (int side = 0; side < 2; ++side) {
+            const sspyr_ctx::Peer& q = h->peer[side];
+            if (!q.attached) continue;
+            const float* pl = q.out + (size_t)first * q.frame_floats + q.off[octave] + (size_t)pi * q.plane[octave];
+            if (side == 0) P.top_halo = pl + (size_t)(q.H[octave] - Rl) * g.pitch;
+            else P.bot_halo = pl;
+        }
     }
     const int R = h->conv[level].radius;
     const int RT = compiled_radius(R);
@@ -107,18 +142,54 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     // strips with the column pass in registers; small ones use the shared-memory tile kernel.
     const long long march_ctas = (long long)((g.W + 511) / 512) * ((g.H + 31) / 32) * count;
     const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && march_ctas >= 2LL * sms));
-    const cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms)
-                                : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
+    // Peer-memory halos: per-octave progress counters.  After level s of build b octave o publishes
+    // (b-1)*CONV_FLAG_STRIDE + s + 1; a level first waits until both neighbours have published the level whose
+    // rows it is about to read (level s-1 of its octave, or level S of the octave above for the decimated base).
+    const bool peered = h->peer[0].attached || h->peer[1].attached;
+    const unsigned epoch = (h->build_seq - 1) * CONV_FLAG_STRIDE;
+    if (peered && !(octave == 0 && level == 0)) {
+        const int wo = (level == 1 && octave > 0) ? octave - 1 : octave;
+        const unsigned need = epoch + (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;
+        for (int side = 0; side < 2; ++side)
+            if (h->peer[side].attached) {
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + wo, 1, need, h->d_flag);
+                ++*launches;
+            }
+    }
+    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms)
+                          : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
+    if (e == cudaSuccess && peered) {
+        conv_signal_kernel<<<1, 1, 0, st>>>(h->d_flag + octave, epoch + (unsigned)level + 1);
+        ++*launches;
+        e = cudaGetLastError();
+    }
     return e;
+}
+
+// Start of a build on a band with attached neighbours: next epoch; nothing of this build may be written before
+// both neighbours have finished reading the previous one (every octave counter at its end-of-build value).
+cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches) {
+    if (!(h->peer[0].attached || h->peer[1].attached)) return cudaSuccess;
+    const unsigned b = ++h->build_seq;
+    if (b >= 2) {
+        const unsigned prev_done = (b - 2) * CONV_FLAG_STRIDE + (unsigned)h->nl;
+        for (int side = 0; side < 2; ++side)
+            if (h->peer[side].attached) {
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag, h->octaves, prev_done, h->d_flag);
+                ++*launches;
+            }
+    }
+    return cudaGetLastError();
 }
 
 // Whole pyramid of one or more frame slots (no row bands: a banded handle is driven level by level so that the
 // host can exchange halos between steps).  Octaves run concurrently: octave o+1 only depends on level S of octave o
 // (its decimated base), so each octave gets its own stream, forked from the handle's stream by events and joined
 // back at the end -- the small octaves' short kernels hide behind the large ones instead of queueing after them.
-cudaError_t launch_conv(const sspyr_ctx* h, int first, int count, int* launches) {
+cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches) {
     const int S = h->cfg.S;
+    if (conv_begin_build(h, h->stream, launches) != cudaSuccess) return cudaGetLastError();
     const bool fork = h->tune.conv_streams != 0 && h->octaves > 1 && !h->aux.empty();
     cudaError_t e;
     if (!fork) {

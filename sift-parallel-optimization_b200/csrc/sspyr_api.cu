@@ -241,7 +241,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
     h->in_pitch_bytes = round_up(in_row, 128);
     h->in_frame_bytes = round_up(h->in_pitch_bytes * cfg.height + 128, 256);
     auto dmalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256); };
-    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * h->frame_floats * cfg.frames)) != cudaSuccess ||
+    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * (h->frame_floats * cfg.frames + 64))) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_in, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_tables, sizeof(float) * h->h_tables.size())) != cudaSuccess) {
         cudaGetLastError();
@@ -273,6 +273,9 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
         }
     }
+    h->d_flag = reinterpret_cast<unsigned*>(h->d_out + h->frame_floats * cfg.frames);   // inside d_out: one IPC handle covers it
+    if ((e = cudaMemset(h->d_flag, 0, 64 * sizeof(float))) != cudaSuccess)
+        return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
     if ((e = cudaMemcpy(h->d_tables, h->h_tables.data(), sizeof(float) * h->h_tables.size(),
                         cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemset(h->d_in, 0, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
@@ -295,6 +298,10 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
 int sspyr_destroy(sspyr_handle h) {
     if (!h) return SSPYR_OK;
     cudaSetDevice(h->device);
+    for (int side = 0; side < 2; ++side) {
+        if (h->peer[side].ipc_out) cudaIpcCloseMemHandle(h->peer[side].ipc_out);
+        if (h->peer[side].ipc_in) cudaIpcCloseMemHandle(h->peer[side].ipc_in);
+    }
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ext) cudaFree(h->d_ext);
     if (h->d_in) cudaFree(h->d_in);
@@ -387,8 +394,12 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
         for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
             e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
     } else {
-        if (h->cfg.full_height != h->cfg.height)
-            return fail(h, SSPYR_ERR_STATE, "a row-band CONV handle is driven level by level: sspyr_conv_step + halo exchange");
+        const bool banded_conv = h->cfg.full_height != h->cfg.height;
+        const bool peers_ok = (!conv_has_up(h) || h->peer[0].attached) && (!conv_has_down(h) || h->peer[1].attached);
+        if (banded_conv && !peers_ok)
+            return fail(h, SSPYR_ERR_STATE, "a row-band CONV handle without attached neighbours is driven level by level: "
+                                            "sspyr_conv_step + halo exchange");
+        if (banded_conv && count != 1) return fail(h, SSPYR_ERR_ARG, "row-band CONV builds one frame slot at a time");
         int done = 0;
         while (done < count && e == cudaSuccess) {           // contiguous own slots share one launch per level
             const int f0 = (first + done) % h->cfg.frames;
@@ -435,6 +446,11 @@ int sspyr_sync(sspyr_handle h) {
     if (!h) return SSPYR_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
+    if (h->peer[0].attached || h->peer[1].attached) {
+        unsigned mark = 0;
+        CU(h, cudaMemcpy(&mark, h->d_flag + 16, sizeof(mark), cudaMemcpyDeviceToHost));
+        if (mark) return fail(h, SSPYR_ERR_STATE, "timed out waiting for a neighbour band (counter value " + std::to_string(mark) + ")");
+    }
     return SSPYR_OK;
 }
 
@@ -618,6 +634,10 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
     if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->nl) return fail(h, SSPYR_ERR_ARG, "bad (octave, level)");
     CU(h, cudaSetDevice(h->device));
     int launches = 0;
+    if (octave == 0 && level == 0) {
+        const cudaError_t e0 = conv_begin_build(h, h->stream, &launches);
+        if (e0 != cudaSuccess) return fail_cuda(h, e0, "kernel launch");
+    }
     const cudaError_t e = launch_conv_step(h, frame, 1, octave, level, h->stream, &launches);
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
     h->last_launches = launches;
@@ -628,6 +648,102 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
         }
         h->built[frame] = 1;
     }
+    return SSPYR_OK;
+}
+
+namespace {
+
+struct IpcBlob {                              // what a neighbour needs to read this band's planes in place
+    uint32_t magic, bytes;
+    int32_t height, width, octaves, nl, frames, pixel_type, mode, pad;
+    uint64_t frame_floats, in_frame_bytes, in_pitch_bytes, flag_off_floats;
+    struct { int32_t H, pitch; uint64_t off, plane; } oct[SSPYR_MAX_OCTAVES];
+    cudaIpcMemHandle_t out, in;
+};
+static_assert(sizeof(IpcBlob) <= SSPYR_IPC_BLOB_BYTES, "blob too large");
+const uint32_t kBlobMagic = 0x53505952u;      // 'SPYR'
+
+int peer_check(sspyr_ctx* h, int side, int width, int octaves, int nl, int frames, int pixel_type, int mode) {
+    if (side != SSPYR_SIDE_ABOVE && side != SSPYR_SIDE_BELOW) return fail(h, SSPYR_ERR_ARG, "bad side");
+    if (h->cfg.mode != SSPYR_MODE_CONV || h->cfg.full_height == h->cfg.height)
+        return fail(h, SSPYR_ERR_STATE, "peer halos are for row-band CONV handles");
+    if ((side == SSPYR_SIDE_ABOVE && !conv_has_up(h)) || (side == SSPYR_SIDE_BELOW && !conv_has_down(h)))
+        return fail(h, SSPYR_ERR_ARG, "this band has no neighbour on that side");
+    if (width != h->cfg.width || octaves != h->octaves || nl != h->nl || frames != h->cfg.frames ||
+        pixel_type != h->cfg.pixel_type || mode != h->cfg.mode)
+        return fail(h, SSPYR_ERR_ARG, "neighbour band has a different configuration");
+    return SSPYR_OK;
+}
+
+}  // namespace
+
+int sspyr_ipc_export(sspyr_handle h, void* blob, size_t capacity, size_t* bytes) {
+    if (!h || !blob) return SSPYR_ERR_ARG;
+    if (capacity < sizeof(IpcBlob)) return fail(h, SSPYR_ERR_ARG, "blob buffer smaller than SSPYR_IPC_BLOB_BYTES");
+    CU(h, cudaSetDevice(h->device));
+    IpcBlob b;
+    std::memset(&b, 0, sizeof(b));
+    b.magic = kBlobMagic;
+    b.bytes = sizeof(IpcBlob);
+    b.height = h->cfg.height; b.width = h->cfg.width; b.octaves = h->octaves; b.nl = h->nl;
+    b.frames = h->cfg.frames; b.pixel_type = h->cfg.pixel_type; b.mode = h->cfg.mode;
+    b.frame_floats = h->frame_floats; b.in_frame_bytes = h->in_frame_bytes; b.in_pitch_bytes = h->in_pitch_bytes;
+    b.flag_off_floats = h->frame_floats * h->cfg.frames;
+    for (int o = 0; o < h->octaves; ++o) {
+        b.oct[o].H = h->oct[o].H; b.oct[o].pitch = h->oct[o].pitch; b.oct[o].off = h->oct[o].off; b.oct[o].plane = h->oct[o].plane;
+    }
+    CU(h, cudaIpcGetMemHandle(&b.out, h->d_out));
+    CU(h, cudaIpcGetMemHandle(&b.in, h->d_in));
+    std::memcpy(blob, &b, sizeof(b));
+    if (bytes) *bytes = sizeof(b);
+    return SSPYR_OK;
+}
+
+int sspyr_ipc_attach(sspyr_handle h, int side, const void* blob, size_t bytes) {
+    if (!h || !blob) return SSPYR_ERR_ARG;
+    if (bytes < sizeof(IpcBlob)) return fail(h, SSPYR_ERR_ARG, "short blob");
+    IpcBlob b;
+    std::memcpy(&b, blob, sizeof(b));
+    if (b.magic != kBlobMagic || b.bytes != sizeof(IpcBlob)) return fail(h, SSPYR_ERR_ARG, "not an sspyr IPC blob");
+    const int rc = peer_check(h, side, b.width, b.octaves, b.nl, b.frames, b.pixel_type, b.mode);
+    if (rc) return rc;
+    CU(h, cudaSetDevice(h->device));
+    sspyr_ctx::Peer& q = h->peer[side];
+    if (q.attached) return fail(h, SSPYR_ERR_STATE, "side already attached");
+    CU(h, cudaIpcOpenMemHandle(&q.ipc_out, b.out, cudaIpcMemLazyEnablePeerAccess));
+    CU(h, cudaIpcOpenMemHandle(&q.ipc_in, b.in, cudaIpcMemLazyEnablePeerAccess));
+    q.out = static_cast<const float*>(q.ipc_out);
+    q.in = static_cast<const unsigned char*>(q.ipc_in);
+    q.flag = reinterpret_cast<const unsigned*>(q.out + b.flag_off_floats);
+    q.height = b.height;
+    q.frame_floats = b.frame_floats;
+    q.in_frame_bytes = b.in_frame_bytes;
+    for (int o = 0; o < h->octaves; ++o) { q.H[o] = b.oct[o].H; q.off[o] = b.oct[o].off; q.plane[o] = b.oct[o].plane; }
+    q.attached = true;
+    return SSPYR_OK;
+}
+
+int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
+    if (!h || !n || h == n) return SSPYR_ERR_ARG;
+    const int rc = peer_check(h, side, n->cfg.width, n->octaves, n->nl, n->cfg.frames, n->cfg.pixel_type, n->cfg.mode);
+    if (rc) return rc;
+    sspyr_ctx::Peer& q = h->peer[side];
+    if (q.attached) return fail(h, SSPYR_ERR_STATE, "side already attached");
+    if (n->device != h->device) {               // bands of one process on two GPUs: plain peer access
+        CU(h, cudaSetDevice(h->device));
+        const cudaError_t e = cudaDeviceEnablePeerAccess(n->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(h, e, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    q.out = n->d_out;
+    q.in = n->d_in;
+    q.flag = n->d_flag;
+    q.height = n->cfg.height;
+    q.frame_floats = n->frame_floats;
+    q.in_frame_bytes = n->in_frame_bytes;
+    for (int o = 0; o < h->octaves; ++o) { q.H[o] = n->oct[o].H; q.off[o] = n->oct[o].off; q.plane[o] = n->oct[o].plane; }
+    q.local = true;
+    q.attached = true;
     return SSPYR_OK;
 }
 

@@ -90,6 +90,21 @@ struct sspyr_ctx {
     size_t halo_off[SSPYR_MAX_OCTAVES] = {0};
     unsigned char* d_halo_raw = nullptr;     // same for the raw frame (octave 0, level 0): [up|down][rmax][in_pitch]
     int halo_rmax = 0;
+    // CONV row bands over peer memory (NVLink): the neighbours' planes are read IN the blur kernel instead of
+    // being copied into d_halo; progress counters in peer memory order the steps (conv_launch.cu).
+    struct Peer {
+        bool attached = false, local = false;
+        const float* out = nullptr;              // neighbour's d_out
+        const unsigned char* in = nullptr;       // neighbour's d_in
+        const unsigned* flag = nullptr;          // neighbour's progress counter
+        void* ipc_out = nullptr;                 // cudaIpcOpenMemHandle results (closed in destroy)
+        void* ipc_in = nullptr;
+        int height = 0, H[SSPYR_MAX_OCTAVES] = {0};
+        size_t off[SSPYR_MAX_OCTAVES] = {0}, plane[SSPYR_MAX_OCTAVES] = {0};
+        size_t frame_floats = 0, in_frame_bytes = 0;
+    } peer[2];                                   // [0] = band above, [1] = band below
+    unsigned* d_flag = nullptr;                  // per-octave progress counters + timeout marker (inside d_out's allocation)
+    unsigned build_seq = 0;                      // builds started so far (all bands issue the same sequence)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::vector<cudaStream_t> aux;           // CONV: one extra stream per octave >= 1
     std::vector<cudaEvent_t> ev_base, ev_done;
@@ -104,7 +119,8 @@ namespace sspyr {
 
 // Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
 cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
-cudaError_t launch_conv(const sspyr_ctx* h, int first_frame, int count, int* launches);
+cudaError_t launch_conv(sspyr_ctx* h, int first_frame, int count, int* launches);
+cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,
                              int* launches);
 bool conv_has_up(const sspyr_ctx* h);

@@ -81,3 +81,47 @@ class DistExchanger:
         for o, s in level_schedule(self.ss):
             self.exchange(o, s, frame)
             self.ss.conv_step(o, s, frame)
+
+
+class LocalPeerLink:
+    """Bands held by several handles of ONE process read each other's planes in place (no copies): every handle
+    attaches its neighbours, then all bands issue the same level steps in lockstep.  On a single GPU the handles
+    must share one stream (the progress-counter waits are then already satisfied when they run)."""
+
+    def __init__(self, handles):
+        self.hs = list(handles)
+        for i, h in enumerate(self.hs):
+            if i > 0:
+                h.peer_attach_local(0, self.hs[i - 1])
+            if i + 1 < len(self.hs):
+                h.peer_attach_local(1, self.hs[i + 1])
+
+    def build(self, frame: int = 0) -> None:
+        for o, s in level_schedule(self.hs[0]):
+            for h in self.hs:
+                h.conv_step(o, s, frame)
+
+
+class PeerExchanger:
+    """One band per rank: neighbours' planes are mapped through CUDA IPC and read inside the blur kernel over
+    NVLink; signal / wait kernels on a counter in peer memory keep the ranks in step.  torch.distributed only
+    carries the 1 KB IPC blobs at start-up -- there is no per-level host-side communication at all."""
+
+    def __init__(self, ss, rank: int, world: int, group=None):
+        import torch.distributed as dist
+        self.ss, self.rank, self.world = ss, rank, world
+        blobs = [None] * world
+        dist.all_gather_object(blobs, ss.ipc_export(), group=group)
+        if rank > 0:
+            ss.ipc_attach(0, blobs[rank - 1])
+        if rank < world - 1:
+            ss.ipc_attach(1, blobs[rank + 1])
+        dist.barrier(group=group)
+
+    def build(self, frame: int = 0) -> None:
+        """One library call: octaves on concurrent streams, per-octave progress counters between the bands."""
+        self.ss.build(frame)
+
+    def build_stepwise(self, frame: int = 0) -> None:
+        for o, s in level_schedule(self.ss):
+            self.ss.conv_step(o, s, frame)

@@ -193,6 +193,19 @@ class ScaleSpace:
     def conv_step(self, octave: int, level: int, frame: int = 0) -> None:
         self._ck(self._lib.sspyr_conv_step(self._h, frame, octave, level))
 
+    # ---- CONV row bands over NVLink peer memory (halo rows read inside the blur kernel) -----------------
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(L.IPC_BLOB_BYTES)
+        n = C.c_size_t()
+        self._ck(self._lib.sspyr_ipc_export(self._h, buf, L.IPC_BLOB_BYTES, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def ipc_attach(self, side: int, blob: bytes) -> None:
+        self._ck(self._lib.sspyr_ipc_attach(self._h, side, blob, len(blob)))
+
+    def peer_attach_local(self, side: int, neighbour: "ScaleSpace") -> None:
+        self._ck(self._lib.sspyr_peer_attach_local(self._h, side, neighbour._h))
+
     def conv_taps(self, level: int) -> np.ndarray:
         buf = np.empty(2 * 64 + 1, dtype=np.float32)
         R = C.c_int()

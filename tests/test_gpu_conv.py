@@ -186,3 +186,36 @@ def test_marching_kernel_on_row_bands(pkg, O, synth):
         want = [ref["gauss"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)]
         check(b.download_gauss(), want, 255.0, f"band@{row0}")
         b.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_bands_reading_neighbour_planes_in_place(pkg, O, synth, world):
+    """Peer-memory halos: the blur kernels read the neighbour band's rows straight out of its planes (what runs
+    over NVLink between GPUs); here all bands live on one GPU and share one stream.  Must equal the exchanged
+    build bit for bit, and the specification within tolerance."""
+    h, w, octs, S = 416, 300, 4, 3
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, S)
+    bands = [pkg.band_rows(h, octs, world, r) for r in range(world)]
+
+    def make():
+        hs = []
+        for row0, rows in bands:
+            ss = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, band_row0=row0, full_height=h)
+            ss.upload(np.ascontiguousarray(img[row0:row0 + rows]))
+            hs.append(ss)
+        return hs
+
+    a, b = make(), make()
+    pkg.LocalExchanger(a).build()
+    link = pkg.LocalPeerLink(b)
+    link.build()
+    link.build()                                              # counters keep counting across frames
+    for (row0, rows), x, y in zip(bands, a, b):
+        y.sync()
+        gx, gy = x.download_gauss(), y.download_gauss()
+        for o in range(octs):
+            np.testing.assert_array_equal(gx[o], gy[o])
+        check(y.download_dog(), [ref["dog"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)], 255.0, "dog")
+        x.close()
+        y.close()
