@@ -289,12 +289,26 @@ def run_native(args) -> dict:
     sampler.active(False)
     dist.barrier()
     my_ms = ev0.elapsed_time(ev1)
+    my_launches = launches[0]                    # kernels launched inside the timed region
     total_ms = dist.max(my_ms)
     ms_per_step = total_ms / steps
 
+    # Second, short pass with a CUDA event pair around EVERY step: median / min per step.  Event records between
+    # launches keep consecutive frames from overlapping, so this is the isolated-step figure, not the throughput.
+    per_step = None
+    if ss is not None:
+        n_ev = max(5, min(50, steps))
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
+        for a, b in evs:
+            a.record(stream)
+            step()
+            b.record(stream)
+        torch.cuda.synchronize()
+        ts = sorted(a.elapsed_time(b) for a, b in evs)
+        per_step = {"median_ms": round(ts[len(ts) // 2], 6), "min_ms": round(ts[0], 6), "n": n_ev,
+                    "note": "isolated steps (event pair per step, no overlap between consecutive frames)"}
     px_per_step_all = float(H) * W * (total_frames if part != "replica" else total_frames * world)
     value = px_per_step_all / (ms_per_step * 1e-3) / 1e6                      # Mpix/s, whole job
-    my_launches = launches[0]
     # roofline of the dominant (only) kernel on this rank: algorithmic bytes per launch / mean launch time
     peak, peak_src = measured_peak()
     work_bytes = frame_bytes
@@ -340,6 +354,8 @@ def run_native(args) -> dict:
                      "b_full_frac": round(frame_bytes * my_frames * steps / (my_ms * 1e-3) / 1e9 / peak, 4) if my_ms else None},
         "clocks": clocks,
     }
+    if per_step:
+        out["per_step_events"] = per_step
     if e2e:
         out["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -393,13 +409,29 @@ def run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my
     sampler.active(False)
     dist.barrier()
     dt = dist.max(dt)
-    mid = h_out[0].numel() // 12                      # centre of octave 0 / DoG_0 (the corners underflow to 0)
-    checksum = float(h_out[0][mid - 512:mid + 512].double().abs().sum())   # the host really holds the result
+    mid = (rows // 2) * width + width // 2            # centre of octave 0 / DoG_0 (REF windows underflow to 0 elsewhere)
+    checksum = float(h_out[0][max(mid - 512, 0):mid + 512].double().abs().sum())   # the host really holds the result
+    # copies alone, per frame (CUDA events on lane 0's stream)
+    ea, eb, ec = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    hs[0].sync()
+    ea.record(streams[0])
+    hs[0].upload_ptr(h_in[0].data_ptr(), width * 4)
+    eb.record(streams[0])
+    hs[0].build()
+    hs[0].sync()
+    eb2 = torch.cuda.Event(enable_timing=True)
+    eb2.record(streams[0])
+    hs[0].download_inplace_ptr(h_out[0].data_ptr())
+    ec.record(streams[0])
+    hs[0].sync()
+    h2d_ms, d2h_ms = ea.elapsed_time(eb), eb2.elapsed_time(ec)
     for h in hs:
         h.close()
     return {"value": round(px_per_step_all * steps / dt / 1e6, 1), "unit": "Mpix/s",
             "h2d_bytes_per_step": int(h2d * my_frames), "d2h_bytes_per_step": int(d2h * my_frames),
             "steps": steps, "ms_per_step": round(dt / steps * 1e3, 4),
+            "h2d_ms_per_frame": round(h2d_ms, 4), "d2h_ms_per_frame": round(d2h_ms, 4),
+            "h2d_GBps": round(h2d / h2d_ms / 1e6, 1), "d2h_GBps": round(d2h / d2h_ms / 1e6, 1),
             "api": "sspyr_upload + sspyr_build + sspyr_download_inplace per frame, pinned host buffers, "
                    "2 handles / 2 streams ping-pong", "result": "reference in-place layout (S+2 DoG + top Gaussian)",
             "checksum": checksum}
@@ -516,6 +548,9 @@ def run_reference(args) -> dict:
             a = O.time_header_variant(p2, S, "a512omp", cores, 2, 10)
             b = O.time_header_variant(p2, S, "a512xp", 7, 2, 10)
             extra["avx512_omp_1024_Mpix_s"] = round(1024 * 1024 / float(np.median(a)) / 1e3, 2)
+            extra["avx512_omp_1024_by_counnt_Mpix_s"] = {
+                str(c): round(1024 * 1024 / float(np.median(O.time_header_variant(p2, S, "a512omp", c, 2, 10))) / 1e3, 2)
+                for c in (1, 2, cores)}    # counnt = 2 is the reference's default (AVX512xOpenMP.h:18)
             extra["avx512_omp_note"] = ("GaussPyramid_a512omp::GenerateDoG_nomp_dynamic, unaligned-store shim, 1024x1024: filters S of "
                                         "S+3 levels, racy DoG -- NOT parity-equivalent, timing only")
             extra["avx512_pthread_1024_Mpix_s"] = round(1024 * 1024 / float(np.median(b)) / 1e3, 2)

@@ -138,10 +138,10 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     const int variant = (h->tune.conv_tall > 0 ? 1 : 0) | (h->tune.conv_pipe > 0 ? 2 : 0);   // default: 32-row, one tile per CTA
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    // Large levels (enough 512-column strips x 32-row segments to fill the GPU in one wave) march down column
-    // strips with the column pass in registers; small ones use the shared-memory tile kernel.
-    const long long march_ctas = (long long)((g.W + 511) / 512) * ((g.H + 31) / 32) * count;
-    const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && march_ctas >= 2LL * sms));
+    // The marching strip kernel (conv_march.cuh) row-filters every input row once and measured faster at every size;
+    // radii above 12 and conv_march = 0 use the one-tile-per-CTA kernel.
+    const long long tiles32 = (long long)((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + 31) / 32) * count;
+    const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && tiles32 >= 6LL * sms));   // default: always
     // Peer-memory halos: per-octave progress counters.  After level s of build b octave o publishes
     // (b-1)*CONV_FLAG_STRIDE + s + 1; a level first waits until both neighbours have published the level whose
     // rows it is about to read (level s-1 of its octave, or level S of the octave above for the decimated base).
@@ -211,6 +211,57 @@ cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches) {
         }
     }
     return cudaSuccess;
+}
+
+void conv_drop_graphs(sspyr_ctx* h) {
+    for (auto& g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+}
+
+// launch_conv, replayed as a CUDA graph from the second build of the same slots on: 26+ small launches and
+// their cross-stream events cost more host time than the small levels take on the GPU.
+cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launches) {
+    const bool peered = h->peer[0].attached || h->peer[1].attached;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (h->tune.conv_graph == 0 || peered || cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess ||
+        cs != cudaStreamCaptureStatusNone)
+        return launch_conv(h, first, count, launches);
+    sspyr_ctx::GraphEntry* ge = nullptr;
+    for (auto& g : h->graphs)
+        if (g.first == first && g.count == count) ge = &g;
+    if (!ge) {
+        h->graphs.push_back({first, count, 0, 0, nullptr});
+        ge = &h->graphs.back();
+    }
+    if (ge->exec) {
+        *launches += ge->launches;
+        return cudaGraphLaunch(ge->exec, h->stream);
+    }
+    if (ge->seen++ == 0) return launch_conv(h, first, count, launches);      // first use: eager (sets kernel attributes)
+    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGetLastError(); return launch_conv(h, first, count, launches); }
+    int n = 0;
+    const cudaError_t le = launch_conv(h, first, count, &n);
+    cudaGraph_t graph = nullptr;
+    e = cudaStreamEndCapture(h->stream, &graph);
+    if (le != cudaSuccess || e != cudaSuccess || !graph) {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        h->tune.conv_graph = 0;                                              // do not try again on this handle
+        return launch_conv(h, first, count, launches);
+    }
+    e = cudaGraphInstantiate(&ge->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        ge->exec = nullptr;
+        cudaGetLastError();
+        h->tune.conv_graph = 0;
+        return launch_conv(h, first, count, launches);
+    }
+    ge->launches = n;
+    *launches += n;
+    return cudaGraphLaunch(ge->exec, h->stream);
 }
 
 cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches) {

@@ -1,56 +1,50 @@
-// csrc/conv_march.cuh -- CONV mode, large levels: column-strip "marching" kernel.
+// csrc/conv_march.cuh -- CONV mode, large levels: the tile kernel made to MARCH down a column strip.
 //
-// Same arithmetic as conv_kernel.cuh (same taps, same row-then-column order, same fp32 FMA chains, so the
-// results are bit-identical), different schedule.  The tile kernel recomputes the row pass for 2R halo rows of
-// every 32-row tile and moves every intermediate through shared memory twice; for big levels that makes it
-// shared-memory- and FMA-bound below the HBM roofline.  Here a thread owns 4 adjacent output columns and
-// marches DOWN a vertical segment of the image:
+// Same arithmetic as conv_kernel.cuh (same taps, same row-then-column order, same fp32 FMA chains: results are
+// bit-identical), different schedule.  The plain tile kernel row-filters TH+2R rows to produce TH output rows
+// (a 1.4-1.6x FMA overhead at TH = 32), its row pass is unbalanced (44 rows x 8 blocks over 256 threads) and
+// every CTA first waits for its own loads.  ncu shows it issue-bound (IPC 0.66, top stall "not selected"), so
+// the only way forward is fewer instructions.  Here a CTA owns a 128-column strip and walks down a vertical
+// segment in steps of 32 rows:
 //
-//   per input row:  128-bit loads of its 4+2R inputs from a shared-memory ring   (row pass, registers only)
-//                   4 x (2R+1) FMAs scatter the row-pass value into a ring of 2R+1 partial output rows held in
-//                   REGISTERS (column pass, no shared memory, no recompute)
-//                   the output row that just completed is stored: G_s, DoG_{s-1} = centre - G_s, decimated base
+//     step k:   wait for the 32 new input rows (cp.async, issued during step k-1's column pass)
+//               row pass of exactly those 32 rows (32 x 8 tasks = one per thread) into sT rows [2R, 2R+32)
+//               issue the cp.async loads of step k+1 (the staging buffer is free again)
+//               column pass + epilogue for 32 output rows out of sT rows [0, 32+2R)
+//               carry the last 2R rows of sT to the top for the next step
 //
-// so shared memory carries each input value once, FMAs are the minimum 2(2R+1) per pixel, and the only
-// redundancy is the 2R warm-up rows at the top of each segment.  The row loop is unrolled 2R+1 times so that
-// the register ring is indexed statically.  Input rows arrive through a cp.async ring of DEPTH batches of 8
-// rows (two batches in flight ahead of the one being filtered); the ring also keeps the BACK batches that
-// still hold the centre rows DoG needs.  A CTA is 4 warps = 512 columns; segments are sized so that the whole
-// grid is co-resident (one wave).  Used for R <= 12 when the level is large enough to fill the GPU this way;
-// everything else goes to the tile kernel.
+// so the row pass runs once per input row (only the 2R warm-up rows of a segment are extra), every thread has
+// the same amount of work in every phase, the loads of the next step overlap the column pass of this one
+// without a second staging buffer, and shared memory per CTA drops to ~44 KB (3-5 CTAs per SM).  The DoG
+// centre values come from a 128-bit re-read of the input row (an L2 hit: the row was staged a few steps ago).
+// Segments are sized so that the grid is about one co-resident wave.
 #pragma once
 #include "conv_kernel.cuh"
 
 namespace sspyr {
 
-constexpr int MARCH_SW = 512;            // strip width per CTA (4 warps x 32 quads x 4 columns)
-constexpr int MARCH_THREADS = 128;
-constexpr int MARCH_NB = 8;              // rows per staging batch
+constexpr int STRIP_TH = 32;             // output rows per step
 
-template <int R> __host__ __device__ constexpr int march_depth() { return (R + MARCH_NB - 1) / MARCH_NB + 3; }
-template <int R> __host__ __device__ constexpr int march_pitch() { return MARCH_SW + 2 * conv_ra<R>(); }
-template <int R> __host__ __device__ constexpr size_t march_smem_bytes() {
-    return sizeof(float) * (size_t)march_depth<R>() * MARCH_NB * march_pitch<R>();
+template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
+    return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t());
 }
 
 namespace {
 
+// Stage input rows gy0 .. gy0+nrows-1 (clamped to the frame, or taken from the neighbour band's halo rows) of the
+// strip starting at column x0 into sIn rows 0..nrows-1.  16-byte chunks that lie inside the row go through
+// cp.async (float planes) or a 128-bit load + convert (raw frames); chunks that straddle the edge are clamped.
 template <int R, int SRC>
-__device__ __forceinline__ void march_stage_batch(const ConvParams& P, float* __restrict__ ring, int b, int total,
-                                                  int y_begin, int x0, size_t fz, int tid) {
+__device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __restrict__ sIn, int gy0, int nrows, int x0,
+                                                 size_t fz, int tid) {
     constexpr int RA = conv_ra<R>();
-    constexpr int PITCH = march_pitch<R>();
-    constexpr int CH = PITCH / 4;                            // 16-byte chunks per staged row
-    constexpr int DEPTH = march_depth<R>();
+    constexpr int PIN = conv_pitch_in<R>();
+    constexpr int CH = (CONV_TW + 2 * RA) / 4;               // 16-byte chunks per staged row
     constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
     const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
-    const int n0 = b * MARCH_NB;
-    float* dst = ring + (size_t)((b % DEPTH) * MARCH_NB) * PITCH;
-    for (int c = tid; c < MARCH_NB * CH; c += MARCH_THREADS) {
+    for (int c = tid; c < nrows * CH; c += CONV_THREADS) {
         const int rr = c / CH, q = c - rr * CH;
-        const int n = n0 + rr;
-        if (n >= total) break;
-        const int gy = y_begin - R + n;
+        const int gy = gy0 + rr;
         const unsigned char* row;
         if (gy < 0) {
             row = P.top_halo ? static_cast<const unsigned char*>(P.top_halo) + (size_t)max(P.halo_rows + gy, 0) * P.src_pitch * elem
@@ -61,7 +55,7 @@ __device__ __forceinline__ void march_stage_batch(const ConvParams& P, float* __
         } else {
             row = src + (size_t)gy * P.src_pitch * elem;
         }
-        float* s = dst + (size_t)rr * PITCH + 4 * q;
+        float* s = sIn + (size_t)rr * PIN + 4 * q;
         const int gx = x0 - RA + 4 * q;
         if (gx >= 0 && gx + 4 <= P.W) {
             if constexpr (SRC == CONV_SRC_PLANE) {
@@ -75,7 +69,7 @@ __device__ __forceinline__ void march_stage_batch(const ConvParams& P, float* __
             } else {
                 *reinterpret_cast<float4*>(s) = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + gx));
             }
-        } else {                                             // chunk straddles the image edge: clamp per element
+        } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
                 s[i] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(row, (size_t)min(max(gx + i, 0), P.W - 1));
@@ -83,140 +77,199 @@ __device__ __forceinline__ void march_stage_batch(const ConvParams& P, float* __
     }
 }
 
-// grid: x = 512-column strips, y = vertical segments of seg_rows output rows, z = frame
-template <int R, int SRC>
-__global__ void __launch_bounds__(MARCH_THREADS)
-conv_march_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
-    constexpr int U = 2 * R + 1;
+// Row pass of `nrows` staged rows: sT[t0 + row][c] = sum_k taps[k] * sIn[row][RA + c + k - R]
+template <int R>
+__device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float* __restrict__ sIn, float* __restrict__ sT,
+                                               int nrows, int t0, int tid) {
     constexpr int RA = conv_ra<R>();
-    constexpr int PITCH = march_pitch<R>();
-    constexpr int DEPTH = march_depth<R>();
-    constexpr int NIN = 4 + 2 * RA;
-    extern __shared__ __align__(16) float ring[];
+    constexpr int PIN = conv_pitch_in<R>();
+    constexpr int PT = conv_pitch_t();
+    constexpr int NB = CONV_TW / CONV_PX;
+    constexpr int NIN = CONV_PX + 2 * RA;
+    for (int task = tid; task < nrows * NB; task += CONV_THREADS) {
+        const int row = task % nrows, cb = task / nrows;          // consecutive lanes -> consecutive rows
+        const float4* in4 = reinterpret_cast<const float4*>(sIn + (size_t)row * PIN + cb * CONV_PX);
+        float in[NIN];
+#pragma unroll
+        for (int q = 0; q < NIN / 4; ++q) {
+            const float4 v = in4[q];
+            in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        }
+        float acc[CONV_PX];
+#pragma unroll
+        for (int i = 0; i < CONV_PX; ++i) acc[i] = 0.0f;
+#pragma unroll
+        for (int k = 0; k <= 2 * R; ++k) {
+            const float w = P.taps[k];
+#pragma unroll
+            for (int i = 0; i < CONV_PX; ++i) acc[i] = fmaf(w, in[i + k + (RA - R)], acc[i]);
+        }
+        float4* out4 = reinterpret_cast<float4*>(sT + (size_t)(t0 + row) * PT + cb * CONV_PX);
+#pragma unroll
+        for (int q = 0; q < CONV_PX / 4; ++q) out4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+}
+
+// grid: x = 128-column strips, y = vertical segments of seg_rows (multiple of 32) output rows, z = frame
+template <int R, int SRC>
+__global__ void __launch_bounds__(CONV_THREADS, 3)
+conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
+    static_assert(2 * R <= STRIP_TH, "the carried rows must fit above the new ones");
+    constexpr int TH = STRIP_TH;
+    constexpr int PIN = conv_pitch_in<R>();
+    constexpr int PT = conv_pitch_t();
+    constexpr int PY = TH / 8;
+    constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
+    extern __shared__ __align__(16) float smem[];
+    float* sIn = smem;                                  // [TH][PIN]     staged input rows (centre at column RA)
+    float* sT = smem + (size_t)TH * PIN;                // [TH+2R][PT]   row-pass results: 2R carried rows + TH new ones
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * MARCH_SW;
+    const int x0 = blockIdx.x * CONV_TW;
     const int y_begin = blockIdx.y * seg_rows;
     const size_t fz = blockIdx.z;
     if (y_begin >= P.H) return;
     const int y_end = min(P.H, y_begin + seg_rows);
-    const int total = (y_end - y_begin) + 2 * R;             // input rows n = 0..total-1  <->  gy = y_begin - R + n
-    const int nbatches = (total + MARCH_NB - 1) / MARCH_NB;
+    const int nsteps = (y_end - y_begin + TH - 1) / TH;
 
-    march_stage_batch<R, SRC>(P, ring, 0, total, y_begin, x0, fz, tid);
+    // warm-up: the 2R rows above the segment
+    strip_stage_rows<R, SRC>(P, sIn, y_begin - R, 2 * R, x0, fz, tid);
     __pipeline_commit();
-    if (nbatches > 1) march_stage_batch<R, SRC>(P, ring, 1, total, y_begin, x0, fz, tid);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    strip_row_pass<R>(P, sIn, sT, 2 * R, 0, tid);
+    __syncthreads();
+    strip_stage_rows<R, SRC>(P, sIn, y_begin + R, TH, x0, fz, tid);
     __pipeline_commit();
 
-    const int x = x0 + 4 * tid;                              // this thread's 4 output columns
-    const int nvalid = P.W - x;                              // <= 0: staging helper only
+    const int cq = tid & 31, rb = tid >> 5;             // column quad / row block of the column pass
+    const int x = x0 + cq * 4;
+    const int nvalid = P.W - x;
     float* g = P.dst_g + fz * P.dst_frame_stride;
     float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
     float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
+    const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
 
-    float acc[U][4];
-#pragma unroll
-    for (int j = 0; j < U; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f;
+    for (int k = 0; k < nsteps; ++k) {
+        __pipeline_wait_prior(0);
+        __syncthreads();                                 // new rows landed; carried rows are in place
+        strip_row_pass<R>(P, sIn, sT, TH, 2 * R, tid);
+        __syncthreads();
+        if (k + 1 < nsteps) strip_stage_rows<R, SRC>(P, sIn, y_begin + R + (k + 1) * TH, TH, x0, fz, tid);
+        __pipeline_commit();                             // in flight during the column pass below
 
-    for (int base = 0; base < total; base += U) {
+        // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
+        const int y0 = y_begin + k * TH;
+        const int yr = y0 + rb * PY;                     // first output row of this thread
+        // centre values for DoG (input rows yr..yr+PY-1, an L2 hit): issued first so that they land during the FMAs
+        float cen[PY][4];
+        if (d && nvalid >= 4) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = base + u;
-            if (n >= total) break;
-            if ((n % MARCH_NB) == 0) {                       // batch boundary (uniform)
-                const int b = n / MARCH_NB;
-                __pipeline_wait_prior(1);                    // batches 0..b have landed (b+1 may be in flight)
-                __syncthreads();                             // ... for every thread, and batch b-1 is fully consumed
-                if (b + 2 < nbatches) march_stage_batch<R, SRC>(P, ring, b + 2, total, y_begin, x0, fz, tid);
-                __pipeline_commit();
+            for (int j = 0; j < PY; ++j) {
+                const unsigned char* crow = src + (size_t)min(yr + j, P.H - 1) * P.src_pitch * elem;
+                if constexpr (SRC == SSPYR_PIXEL_I32) {
+                    const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(crow) + x));
+                    cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                } else if constexpr (SRC == SSPYR_PIXEL_U8) {
+                    const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
+                    cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                } else {
+                    const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
+                    cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                }
             }
-            // ---- row pass: t[i] = sum_k taps[k] * in[x + i + k - R] ----
-            const float* srow = ring + (size_t)(((n / MARCH_NB) % DEPTH) * MARCH_NB + (n % MARCH_NB)) * PITCH + 4 * tid;
-            float in[NIN];
+        }
+        const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
+        float acc[PY][4];
 #pragma unroll
-            for (int q = 0; q < NIN / 4; ++q) {
-                const float4 v = *reinterpret_cast<const float4*>(srow + 4 * q);
-                in[4 * q] = v.x; in[4 * q + 1] = v.y; in[4 * q + 2] = v.z; in[4 * q + 3] = v.w;
+        for (int j = 0; j < PY; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+#pragma unroll
+        for (int i = 0; i < PY + 2 * R; ++i) {
+            const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                if (i - j >= 0 && i - j <= 2 * R) {
+                    const float w = P.taps[i - j];
+                    acc[j][0] = fmaf(w, v.x, acc[j][0]);
+                    acc[j][1] = fmaf(w, v.y, acc[j][1]);
+                    acc[j][2] = fmaf(w, v.z, acc[j][2]);
+                    acc[j][3] = fmaf(w, v.w, acc[j][3]);
+                }
             }
-            float t[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        }
+        if (nvalid >= 4) {                               // full quad: vector stores, one running offset
+            unsigned o = (unsigned)yr * (unsigned)P.dst_pitch + (unsigned)x;   // a plane has < 2^32 floats
 #pragma unroll
-            for (int k = 0; k <= 2 * R; ++k) {
-                const float w = P.taps[k];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) t[i] = fmaf(w, in[i + k + (RA - R)], t[i]);
-            }
-            // ---- column pass: out(j) += taps[k] * T(n) for j = n - k; slot(j) = j mod U is static here ----
-            // (k descending so that each output accumulates its rows top to bottom, as the tile kernel does)
-#pragma unroll
-            for (int k = 2 * R; k >= 0; --k) {
-                constexpr int dummy = 0; (void)dummy;
-                const int slot = ((u - k) % U + U) % U;
-                const float w = P.taps[k];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[slot][i] = fmaf(w, t[i], acc[slot][i]);
-            }
-            // ---- output row j = n - 2R is complete: slot (u + 1) % U ----
-            {
-                constexpr int dummy2 = 0; (void)dummy2;
-                const int slot = (u + 1) % U;
-                const int j = n - 2 * R;
-                if (j >= 0 && nvalid > 0) {
-                    const int y = y_begin + j;
-                    const size_t o = (size_t)y * P.dst_pitch + x;
-                    if (nvalid >= 4) {
-                        *reinterpret_cast<float4*>(g + o) = make_float4(acc[slot][0], acc[slot][1], acc[slot][2], acc[slot][3]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) if (i < nvalid) g[o + i] = acc[slot][i];
-                    }
-                    if (d) {                                 // DoG_{s-1} = G_{s-1} - G_s; centre row = input row n - R
-                        const int nc = n - R;
-                        const float4 c = *reinterpret_cast<const float4*>(
-                            ring + (size_t)(((nc / MARCH_NB) % DEPTH) * MARCH_NB + (nc % MARCH_NB)) * PITCH + RA + 4 * tid);
-                        const float dv[4] = {c.x - acc[slot][0], c.y - acc[slot][1], c.z - acc[slot][2], c.w - acc[slot][3]};
-                        if (nvalid >= 4) {
-                            __stcs(reinterpret_cast<float4*>(d + o), make_float4(dv[0], dv[1], dv[2], dv[3]));
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) if (i < nvalid) __stcs(d + o + i, dv[i]);
-                        }
-                    }
-                    if (dec && (y & 1) == 0) {               // even-phase decimation (GuassDePyramid.h:80)
-                        const int dy = y >> 1, dx = x >> 1;
-                        if (dy < P.dec_H && dx < P.dec_W) {
-                            float* q = dec + (size_t)dy * P.dec_pitch + dx;
-                            if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[slot][0], acc[slot][2]);
-                            else q[0] = acc[slot][0];
-                        }
+            for (int j = 0; j < PY; ++j, o += (unsigned)P.dst_pitch) {
+                const int y = yr + j;
+                if (y >= y_end) break;
+                *reinterpret_cast<float4*>(g + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                if (d)                                   // DoG_{s-1} = G_{s-1} - G_s  (GuassDePyramid.h:143)
+                    __stcs(reinterpret_cast<float4*>(d + o), make_float4(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1],
+                                                                         cen[j][2] - acc[j][2], cen[j][3] - acc[j][3]));
+                if (dec && (y & 1) == 0) {               // even-phase decimation (GuassDePyramid.h:80)
+                    const int dy = y >> 1, dx = x >> 1;
+                    if (dy < P.dec_H && dx < P.dec_W) {
+                        float* q = dec + (size_t)dy * P.dec_pitch + dx;
+                        if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
+                        else q[0] = acc[j][0];
                     }
                 }
-                acc[slot][0] = acc[slot][1] = acc[slot][2] = acc[slot][3] = 0.0f;
             }
+        } else if (nvalid > 0) {                         // ragged right edge: element by element
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                const int y = yr + j;
+                if (y >= y_end) break;
+                const size_t o = (size_t)y * P.dst_pitch + x;
+                const unsigned char* crow = src + (size_t)y * P.src_pitch * elem;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nvalid) {
+                        g[o + i] = acc[j][i];
+                        if (d) __stcs(d + o + i, load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(crow, (size_t)(x + i)) - acc[j][i]);
+                    }
+                if (dec && (y & 1) == 0) {
+                    const int dy = y >> 1, dx = x >> 1;
+                    if (dy < P.dec_H && dx < P.dec_W) {
+                        float* q = dec + (size_t)dy * P.dec_pitch + dx;
+                        q[0] = acc[j][0];
+                        if (dx + 1 < P.dec_W && nvalid > 2) q[1] = acc[j][2];
+                    }
+                }
+            }
+        }
+        __syncthreads();                                 // every column pass has read the rows about to be replaced
+        // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH)
+        for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CONV_THREADS) {
+            const int rr = c / (CONV_TW / 4), q = c - rr * (CONV_TW / 4);
+            *reinterpret_cast<float4*>(sT + (size_t)rr * PT + 4 * q) = *reinterpret_cast<const float4*>(sT + (size_t)(TH + rr) * PT + 4 * q);
         }
     }
 }
 
 template <int R, int SRC>
 cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms) {
-    constexpr size_t smem = march_smem_bytes<R>();
+    constexpr size_t smem = strip_smem_bytes<R>();
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_march_kernel<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) configured[device] = true;
     }
     int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-    const int strips = (P.W + MARCH_SW - 1) / MARCH_SW;
-    // one co-resident wave: as many vertical segments as fit, each at least 32 rows
-    long long segs = (long long)sms * per_sm / ((long long)strips * frames);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);          // 4 CTAs of 256 threads at <= 64 registers
+    const int strips = (P.W + CONV_TW - 1) / CONV_TW;
+    // about `waves` co-resident waves of CTAs: vertical segments of a multiple of 32 rows, at least 64
+    const int waves = 2;
+    long long segs = (long long)sms * per_sm * waves / ((long long)strips * frames);
     if (segs < 1) segs = 1;
     int seg_rows = (int)((P.H + segs - 1) / segs);
-    if (seg_rows < 32) seg_rows = 32;
-    seg_rows = (seg_rows + 1) & ~1;                           // even: decimation rows stay aligned with segments
+    seg_rows = (seg_rows + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
+    if (seg_rows < 2 * STRIP_TH) seg_rows = 2 * STRIP_TH;
     const int nseg = (P.H + seg_rows - 1) / seg_rows;
     const dim3 grid(strips, nseg, frames);
-    conv_march_kernel<R, SRC><<<grid, MARCH_THREADS, smem, st>>>(P, seg_rows);
+    conv_strip_kernel<R, SRC><<<grid, CONV_THREADS, smem, st>>>(P, seg_rows);
     return cudaGetLastError();
 }
 

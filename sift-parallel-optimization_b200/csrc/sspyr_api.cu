@@ -308,6 +308,7 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
+    conv_drop_graphs(h);
     for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_done) if (ev) cudaEventDestroy(ev);
@@ -349,6 +350,7 @@ int sspyr_algorithmic_bytes(sspyr_handle h, uint64_t* bytes) {
 
 int sspyr_set_stream(sspyr_handle h, void* cuda_stream) {
     if (!h) return SSPYR_ERR_ARG;
+    conv_drop_graphs(h);
     h->stream = static_cast<cudaStream_t>(cuda_stream);
     return SSPYR_OK;
 }
@@ -362,6 +364,7 @@ int sspyr_upload(sspyr_handle h, int frame, const void* host, size_t pitch_bytes
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemcpy2DAsync(h->d_in + (size_t)frame * h->in_frame_bytes, h->in_pitch_bytes, host, pitch_bytes,
                             row, h->cfg.height, cudaMemcpyHostToDevice, h->stream));
+    if (h->ext_in[frame]) conv_drop_graphs(h);
     h->ext_in[frame] = nullptr;
     h->built[frame] = 0;
     return SSPYR_OK;
@@ -376,6 +379,7 @@ int sspyr_set_input_device(sspyr_handle h, int frame, const void* dev, size_t pi
         if (pitch_bytes < row || pitch_bytes % 16 || reinterpret_cast<uintptr_t>(dev) % 16)
             return fail(h, SSPYR_ERR_ARG, "device image must be 16-byte aligned with a pitch that is a multiple of 16 bytes");
     }
+    if (h->ext_in[frame] != dev || h->ext_pitch[frame] != pitch_bytes) conv_drop_graphs(h);   // pointers are baked in
     h->ext_in[frame] = dev;
     h->ext_pitch[frame] = pitch_bytes;
     h->built[frame] = 0;
@@ -406,7 +410,7 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
             int n = 1;
             if (!h->ext_in[f0])
                 while (done + n < count && f0 + n < h->cfg.frames && !h->ext_in[f0 + n]) ++n;
-            e = launch_conv(h, f0, n, &launches);
+            e = launch_conv_graphed(h, f0, n, &launches);
             done += n;
         }
         for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
@@ -749,6 +753,7 @@ int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
 
 int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     if (!h || !key) return SSPYR_ERR_ARG;
+    conv_drop_graphs(h);
     if (!std::strcmp(key, "rows_per_thread")) h->tune.rows_per_thread = value;
     else if (!std::strcmp(key, "block")) h->tune.block = value;
     else if (!std::strcmp(key, "bx")) h->tune.bx = value;
@@ -759,6 +764,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_streams")) h->tune.conv_streams = value;
     else if (!std::strcmp(key, "conv_pipe")) h->tune.conv_pipe = value;
     else if (!std::strcmp(key, "conv_march")) h->tune.conv_march = value;
+    else if (!std::strcmp(key, "conv_graph")) h->tune.conv_graph = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
     return SSPYR_OK;
 }

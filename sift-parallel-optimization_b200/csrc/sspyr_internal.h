@@ -53,7 +53,8 @@ struct Tuning {
     int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
     int conv_tall = 0;         // CONV: 64-row tiles (radii <= 6)
     int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
-    int conv_march = 0;        // CONV: column-strip marching kernel (R <= 12): 1 on, -1 by level size; measured slower (profiles/)
+    int conv_march = 1;        // CONV: marching strip kernel for radii <= 12 (0 = one-tile-per-CTA kernel everywhere)
+    int conv_graph = 1;        // CONV: replay the per-frame launch sequence as a CUDA graph from its 2nd use on
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
                                // launches stop them from overlapping, so this is off unless asked for
@@ -106,6 +107,8 @@ struct sspyr_ctx {
     unsigned* d_flag = nullptr;                  // per-octave progress counters + timeout marker (inside d_out's allocation)
     unsigned build_seq = 0;                      // builds started so far (all bands issue the same sequence)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    struct GraphEntry { int first, count, seen, launches; cudaGraphExec_t exec; };
+    std::vector<GraphEntry> graphs;          // CONV: captured whole-pyramid launch sequences, by (first slot, count)
     std::vector<cudaStream_t> aux;           // CONV: one extra stream per octave >= 1
     std::vector<cudaEvent_t> ev_base, ev_done;
     bool timed = false;
@@ -121,6 +124,8 @@ namespace sspyr {
 cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
 cudaError_t launch_conv(sspyr_ctx* h, int first_frame, int count, int* launches);
 cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches);
+cudaError_t launch_conv_graphed(sspyr_ctx* h, int first_frame, int count, int* launches);
+void conv_drop_graphs(sspyr_ctx* h);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,
                              int* launches);
 bool conv_has_up(const sspyr_ctx* h);
