@@ -259,3 +259,31 @@ def test_full_size_4k_frame_and_properties(pkg, O, synth):
             np.testing.assert_array_equal(a[o][:5], gg[o][:5] - gg[o][1:])
             normal = np.abs(a[o]) > 1e-30                                # x2 is exact away from denormals
             np.testing.assert_array_equal(b[o][normal], 2 * a[o][normal])
+
+
+@pytest.mark.parametrize("mode_name", ["ref", "conv"])
+@pytest.mark.parametrize("h,w,octs", [(135, 241, 4), (67, 515, 3), (200, 96, 5)])
+def test_kernels_never_write_outside_the_level_rectangles(pkg, synth, mode_name, h, w, octs):
+    """Own bounds check (compute-sanitizer is closed on this pool): fill the whole frame slot with a sentinel,
+    build, and require every byte outside the H_o x W_o rectangles -- row padding up to the 128-byte pitch --
+    to still hold it, while every in-range output was written."""
+    import torch
+    from sift_parallel_optimization_b200.exchange import device_view
+    mode = pkg.MODE_REF if mode_name == "ref" else pkg.MODE_CONV
+    S = 3
+    with pkg.ScaleSpace(h, w, octs, S, mode=mode) as ss:
+        dims = [ss.level_dims(o) for o in range(octs)]
+        floats = sum((2 * (S + 3) - 1) * r * p for r, _, p in dims)
+        base = ss.device_ptr(0, 0, pkg.KIND_GAUSS)
+        slot = device_view(base, floats * 4, torch.device("cuda", torch.cuda.current_device())).view(torch.int32)
+        slot.fill_(-1)                                            # 0xFFFFFFFF: a NaN no kernel produces
+        ss.upload(synth.noise(h, w))
+        ss.build()
+        ss.sync()
+        host = slot.cpu().numpy()
+        off = 0
+        for r, c, p in dims:
+            planes = host[off:off + (2 * (S + 3) - 1) * r * p].reshape(2 * (S + 3) - 1, r, p)
+            assert np.all(planes[:, :, c:] == -1), "a kernel wrote into the row padding"
+            assert not np.any(planes[:, :, :c] == -1), "an output pixel was never written"
+            off += planes.size
