@@ -9,6 +9,11 @@
 #define SSPYR_CAT(a, b) SSPYR_CAT2(a, b)
 
 namespace sspyr {
+#if SSPYR_NL == 6
+cudaError_t launch_ref_prefetch(const void* img, size_t pitch_bytes, int row_bytes, int rows, cudaStream_t st) {
+    return launch_prefetch(img, pitch_bytes, row_bytes, rows, st);
+}
+#endif
 cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, dim3 grid, dim3 block,
                                                cudaStream_t st, bool pdl) {
     return launch_pix<SSPYR_NL>(P, pix, rpt, grid, block, st, pdl);

@@ -276,6 +276,36 @@ ref_fused_kernel(const __grid_constant__ RefParams P) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
+// Pull the rows of a frame toward L2 (one 128-byte line per thread, evict-last): issued for the NEXT frame slot
+// while the current one is being built, so that the build kernel's input loads are L2 hits and the DRAM sees the
+// reads as one dense burst instead of a trickle between its writes.
+__global__ void __launch_bounds__(256)
+ref_prefetch_kernel(const unsigned char* __restrict__ img, unsigned long long pitch_bytes, int row_bytes, int rows) {
+    asm volatile("griddepcontrol.launch_dependents;");
+    const int lines = (row_bytes + 127) >> 7;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < (long long)lines * rows) {
+        const int r = (int)(t / lines), l = (int)(t - (long long)r * lines);
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(img + (size_t)r * pitch_bytes + ((size_t)l << 7)));
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+inline cudaError_t launch_prefetch(const void* img, size_t pitch_bytes, int row_bytes, int rows, cudaStream_t st) {
+    const long long n = (long long)((row_bytes + 127) >> 7) * rows;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)((n + 255) / 256));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, ref_prefetch_kernel, static_cast<const unsigned char*>(img),
+                              (unsigned long long)pitch_bytes, row_bytes, rows);
+}
+
 template <int NL, int PIX, int RPT>
 cudaError_t launch_one(const RefParams& P, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg{};

@@ -7,6 +7,7 @@ namespace sspyr {
 #define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, dim3, dim3, cudaStream_t, bool);
 SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 #undef SSPYR_DECL
+cudaError_t launch_ref_prefetch(const void* img, size_t pitch_bytes, int row_bytes, int rows, cudaStream_t st);
 
 namespace {
 
@@ -105,6 +106,16 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
         if (e != cudaSuccess) return e;
         ++*launches;
         done += n;
+    }
+    const bool auto_pf = h->tune.prefetch_next < 0 && frames > 1 && h->in_frame_bytes <= (48u << 20) &&
+                         h->in_frame_bytes >= (4u << 20);   // tiny frames are launch-bound: an extra launch costs more
+    if (h->tune.prefetch_next > 0 || auto_pf) {  // warm L2 with the slot that is most likely built next
+        const int nf = (first + count) % frames;
+        size_t pitch_bytes = 0;
+        const void* img = frame_input(h, nf, &pitch_bytes);
+        const cudaError_t e = launch_ref_prefetch(img, pitch_bytes, (int)((size_t)h->cfg.width * h->elem_bytes), h->cfg.height, h->stream);
+        if (e != cudaSuccess) return e;
+        ++*launches;
     }
     return cudaSuccess;
 }

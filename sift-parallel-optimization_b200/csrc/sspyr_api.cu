@@ -759,6 +759,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "bx")) h->tune.bx = value;
     else if (!std::strcmp(key, "pdl")) h->tune.pdl = value;
     else if (!std::strcmp(key, "occ")) h->tune.occ = value;
+    else if (!std::strcmp(key, "prefetch_next")) h->tune.prefetch_next = value;
     else if (!std::strcmp(key, "timing")) h->tune.timing = value;
     else if (!std::strcmp(key, "conv_tall")) h->tune.conv_tall = value;
     else if (!std::strcmp(key, "conv_streams")) h->tune.conv_streams = value;

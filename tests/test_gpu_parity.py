@@ -175,7 +175,7 @@ def test_frame_slots_batch_and_rebuild(pkg, O, synth):
         for f in range(n):
             ss.upload(frames[f], frame=f)
         ss.build_batch(0, n)
-        assert ss.last_launches() == 1                                       # one launch for the batch
+        assert ss.last_launches() == 1                                       # one launch for the batch (small frames: no L2 prefetch)
         for f in (0, 3, 4):
             ref = O.ref_build(frames[f], octaves=3, S=3)["inplace"]
             for o, a in enumerate(ss.download_inplace(frame=f)):
