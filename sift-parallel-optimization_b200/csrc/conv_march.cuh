@@ -31,18 +31,19 @@ template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
 
 namespace {
 
-// Stage input rows gy0 .. gy0+nrows-1 (clamped to the frame, or taken from the neighbour band's halo rows) of the
-// strip starting at column x0 into sIn rows 0..nrows-1.  16-byte chunks that lie inside the row go through
+// Stage input rows gy0 .. gy0+NROWS-1 (clamped to the frame, or taken from the neighbour band's halo rows) of the
+// strip starting at column x0 into sIn rows 0..NROWS-1.  16-byte chunks that lie inside the row go through
 // cp.async (float planes) or a 128-bit load + convert (raw frames); chunks that straddle the edge are clamped.
-template <int R, int SRC>
-__device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __restrict__ sIn, int gy0, int nrows, int x0,
-                                                 size_t fz, int tid) {
+// (A warp-per-row variant with the row pointer hoisted was measured 15 % slower: fewer copies in flight.)
+template <int R, int SRC, int NROWS>
+__device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __restrict__ sIn, int gy0, int x0,
+                                                 const unsigned char* __restrict__ src, int tid) {
     constexpr int RA = conv_ra<R>();
     constexpr int PIN = conv_pitch_in<R>();
-    constexpr int CH = (CONV_TW + 2 * RA) / 4;               // 16-byte chunks per staged row
+    constexpr int CH = (CONV_TW + 2 * RA) / 4;               // 16-byte chunks per staged row (34..40)
     constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
-    const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
-    for (int c = tid; c < nrows * CH; c += CONV_THREADS) {
+#pragma unroll 1
+    for (int c = tid; c < NROWS * CH; c += CONV_THREADS) {       // chunks dealt linearly: every thread has 4-5 in flight
         const int rr = c / CH, q = c - rr * CH;
         const int gy = gy0 + rr;
         const unsigned char* row;
@@ -55,7 +56,7 @@ __device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __r
         } else {
             row = src + (size_t)gy * P.src_pitch * elem;
         }
-        float* s = sIn + (size_t)rr * PIN + 4 * q;
+        float* s = sIn + rr * PIN + 4 * q;
         const int gx = x0 - RA + 4 * q;
         if (gx >= 0 && gx + 4 <= P.W) {
             if constexpr (SRC == CONV_SRC_PLANE) {
@@ -77,18 +78,18 @@ __device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __r
     }
 }
 
-// Row pass of `nrows` staged rows: sT[t0 + row][c] = sum_k taps[k] * sIn[row][RA + c + k - R]
-template <int R>
-__device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float* __restrict__ sIn, float* __restrict__ sT,
-                                               int nrows, int t0, int tid) {
+// Row pass of NROWS staged rows: sT[T0 + row][c] = sum_k taps[k] * sIn[row][RA + c + k - R]
+template <int R, int NROWS, int T0>
+__device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float* __restrict__ sIn, float* __restrict__ sT, int tid) {
     constexpr int RA = conv_ra<R>();
     constexpr int PIN = conv_pitch_in<R>();
     constexpr int PT = conv_pitch_t();
     constexpr int NB = CONV_TW / CONV_PX;
     constexpr int NIN = CONV_PX + 2 * RA;
-    for (int task = tid; task < nrows * NB; task += CONV_THREADS) {
-        const int row = task % nrows, cb = task / nrows;          // consecutive lanes -> consecutive rows
-        const float4* in4 = reinterpret_cast<const float4*>(sIn + (size_t)row * PIN + cb * CONV_PX);
+#pragma unroll 1
+    for (int task = tid; task < NROWS * NB; task += CONV_THREADS) {
+        const int row = task % NROWS, cb = task / NROWS;          // consecutive lanes -> consecutive rows (compile-time NROWS)
+        const float4* in4 = reinterpret_cast<const float4*>(sIn + row * PIN + cb * CONV_PX);
         float in[NIN];
 #pragma unroll
         for (int q = 0; q < NIN / 4; ++q) {
@@ -104,7 +105,7 @@ __device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float*
 #pragma unroll
             for (int i = 0; i < CONV_PX; ++i) acc[i] = fmaf(w, in[i + k + (RA - R)], acc[i]);
         }
-        float4* out4 = reinterpret_cast<float4*>(sT + (size_t)(t0 + row) * PT + cb * CONV_PX);
+        float4* out4 = reinterpret_cast<float4*>(sT + (T0 + row) * PT + cb * CONV_PX);
 #pragma unroll
         for (int q = 0; q < CONV_PX / 4; ++q) out4[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
     }
@@ -132,14 +133,16 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
     const int y_end = min(P.H, y_begin + seg_rows);
     const int nsteps = (y_end - y_begin + TH - 1) / TH;
 
+    const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
+
     // warm-up: the 2R rows above the segment
-    strip_stage_rows<R, SRC>(P, sIn, y_begin - R, 2 * R, x0, fz, tid);
+    strip_stage_rows<R, SRC, 2 * R>(P, sIn, y_begin - R, x0, src, tid);
     __pipeline_commit();
     __pipeline_wait_prior(0);
     __syncthreads();
-    strip_row_pass<R>(P, sIn, sT, 2 * R, 0, tid);
+    strip_row_pass<R, 2 * R, 0>(P, sIn, sT, tid);
     __syncthreads();
-    strip_stage_rows<R, SRC>(P, sIn, y_begin + R, TH, x0, fz, tid);
+    strip_stage_rows<R, SRC, TH>(P, sIn, y_begin + R, x0, src, tid);
     __pipeline_commit();
 
     const int cq = tid & 31, rb = tid >> 5;             // column quad / row block of the column pass
@@ -148,14 +151,14 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
     float* g = P.dst_g + fz * P.dst_frame_stride;
     float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
     float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
-    const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
 
+#pragma unroll 1
     for (int k = 0; k < nsteps; ++k) {
         __pipeline_wait_prior(0);
         __syncthreads();                                 // new rows landed; carried rows are in place
-        strip_row_pass<R>(P, sIn, sT, TH, 2 * R, tid);
+        strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
         __syncthreads();
-        if (k + 1 < nsteps) strip_stage_rows<R, SRC>(P, sIn, y_begin + R + (k + 1) * TH, TH, x0, fz, tid);
+        if (k + 1 < nsteps) strip_stage_rows<R, SRC, TH>(P, sIn, y_begin + R + (k + 1) * TH, x0, src, tid);
         __pipeline_commit();                             // in flight during the column pass below
 
         // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
