@@ -2,7 +2,9 @@
 // between octaves, row-band halo staging, and the DoG extremum scan.  Also the halo part of the C ABI.
 #include <cstring>
 
-#include "conv_kernel.cuh"
+#include <cudaTypedefs.h>
+
+#include "conv_march.cuh"
 
 namespace sspyr {
 
@@ -11,7 +13,9 @@ SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_DECL(14) SSPYR_DECL(15) SSPYR_DECL(16)
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 #undef SSPYR_DECL
-#define SSPYR_DECL(n) cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int);
+#define SSPYR_DECL(n)                                                                                  \
+    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int, const CUtensorMap*); \
+    int march_box_cols_r##n();
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
 #undef SSPYR_DECL
@@ -55,14 +59,51 @@ cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cud
     }
 }
 
-cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms) {
+cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
+                           const CUtensorMap* tmap) {
     switch (r) {
-#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms);
+#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms, tmap);
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
 #undef SSPYR_CASE
         default: return cudaErrorInvalidValue;
     }
+}
+
+int march_box_cols(int r) {
+    switch (r) {
+#define SSPYR_CASE(n) case n: return march_box_cols_r##n();
+        SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
+        SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
+#undef SSPYR_CASE
+        default: return 0;
+    }
+}
+
+// Tensor map of a float plane for the strip kernel's TMA staging: (columns = row pitch, rows, frame slots),
+// box = box_cols x 32 x 1, no swizzle, zero fill (never relied on: edge steps do not use TMA).
+bool make_plane_tensor_map(CUtensorMap* map, const float* plane0, int pitch, int rows, int frames, size_t frame_floats,
+                           int box_cols) {
+    static PFN_cuTensorMapEncodeTiled encode = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+        cudaGetLastError();
+    }
+    if (!encode || box_cols <= 0 || box_cols > 256 || pitch < box_cols) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)(frames > 0 ? frames : 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)frame_floats * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)STRIP_TH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (rows < STRIP_TH) return false;
+    return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane0), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace
@@ -156,7 +197,13 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 ++*launches;
             }
     }
-    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms)
+    // TMA staging for float-plane sources: the map covers the frames of this launch (frame = 3rd coordinate)
+    CUtensorMap tmap;
+    const CUtensorMap* tm = nullptr;
+    if (march && src_kind == CONV_SRC_PLANE && h->tune.conv_tma != 0 &&
+        make_plane_tensor_map(&tmap, static_cast<const float*>(P.src), g.pitch, g.H, count, h->frame_floats, march_box_cols(R)))
+        tm = &tmap;
+    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms, tm)
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered) {

@@ -19,14 +19,48 @@
 // centre values come from a 128-bit re-read of the input row (an L2 hit: the row was staged a few steps ago).
 // Segments are sized so that the grid is about one co-resident wave.
 #pragma once
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "conv_kernel.cuh"
 
 namespace sspyr {
 
 constexpr int STRIP_TH = 32;             // output rows per step
 
+// ---- TMA (cp.async.bulk.tensor) + mbarrier helpers --------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+// Bounded wait (a lost TMA must not hang the GPU): returns false on time-out.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+
+// One 3-D box (columns, rows, frame) of the source plane -> shared memory, completion on `bar`.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
+                   "r"(smem_u32(bar)) : "memory");
+}
+
 template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
-    return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t());
+    return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t()) + 16;   // + mbarrier
 }
 
 namespace {
@@ -112,18 +146,25 @@ __device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float*
 }
 
 // grid: x = 128-column strips, y = vertical segments of seg_rows (multiple of 32) output rows, z = frame
-template <int R, int SRC>
+// TMA = true (float-plane sources): the 32-row x PIN-column box of every interior step is fetched by ONE
+// cp.async.bulk.tensor issued by one thread and tracked by an mbarrier, instead of ~1200 cp.async from all threads.
+// Steps that touch the frame edge (clamp-to-edge is not a TMA fill mode) or a neighbour band's halo rows keep
+// the cp.async path.
+template <int R, int SRC, bool TMA>
 __global__ void __launch_bounds__(CONV_THREADS, 3)
-conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
+conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __grid_constant__ CUtensorMap tmap) {
     static_assert(2 * R <= STRIP_TH, "the carried rows must fit above the new ones");
     constexpr int TH = STRIP_TH;
     constexpr int PIN = conv_pitch_in<R>();
     constexpr int PT = conv_pitch_t();
     constexpr int PY = TH / 8;
     constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     float* sIn = smem;                                  // [TH][PIN]     staged input rows (centre at column RA)
     float* sT = smem + (size_t)TH * PIN;                // [TH+2R][PT]   row-pass results: 2R carried rows + TH new ones
+    // mbarrier of the TMA staging: kept in the dynamic allocation so that sIn stays at its 128-byte aligned base
+    unsigned long long& bar = *reinterpret_cast<unsigned long long*>(sT + (size_t)(TH + 2 * R) * PT);
+    constexpr int RA_ = conv_ra<R>();
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * CONV_TW;
@@ -134,6 +175,29 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
     const int nsteps = (y_end - y_begin + TH - 1) / TH;
 
     const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
+    // a step may use TMA when its whole box lies inside the plane: needed columns inside [0, W), the 4-column
+    // overshoot of the padded box inside the row pitch, rows inside [0, H)
+    const bool tma_cols = TMA && x0 - RA_ >= 0 && x0 + CONV_TW + RA_ <= P.W && x0 - RA_ + PIN <= P.src_pitch;
+    unsigned phase = 0;
+    bool pending_tma = false;
+    if (TMA) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+    }
+    auto stage_step = [&](int gy0) {                     // rows gy0 .. gy0+TH-1 -> sIn
+        if (TMA && tma_cols && gy0 >= 0 && gy0 + TH <= P.H) {
+            if (tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of sIn are done
+                mbar_expect_tx(&bar, (unsigned)(TH * PIN * sizeof(float)));
+                tma_load_3d(sIn, &tmap, x0 - RA_, gy0, (int)fz, &bar);
+            }
+            pending_tma = true;
+        } else {
+            strip_stage_rows<R, SRC, TH>(P, sIn, gy0, x0, src, tid);
+            pending_tma = false;
+        }
+        __pipeline_commit();
+    };
 
     // warm-up: the 2R rows above the segment
     strip_stage_rows<R, SRC, 2 * R>(P, sIn, y_begin - R, x0, src, tid);
@@ -142,8 +206,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
     __syncthreads();
     strip_row_pass<R, 2 * R, 0>(P, sIn, sT, tid);
     __syncthreads();
-    strip_stage_rows<R, SRC, TH>(P, sIn, y_begin + R, x0, src, tid);
-    __pipeline_commit();
+    stage_step(y_begin + R);
 
     const int cq = tid & 31, rb = tid >> 5;             // column quad / row block of the column pass
     const int x = x0 + cq * 4;
@@ -154,12 +217,16 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
 
 #pragma unroll 1
     for (int k = 0; k < nsteps; ++k) {
-        __pipeline_wait_prior(0);
+        if (pending_tma) {
+            if (!mbar_wait(&bar, phase)) return;         // (bounded; never observed)
+            phase ^= 1;
+        } else {
+            __pipeline_wait_prior(0);
+        }
         __syncthreads();                                 // new rows landed; carried rows are in place
         strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
         __syncthreads();
-        if (k + 1 < nsteps) strip_stage_rows<R, SRC, TH>(P, sIn, y_begin + R + (k + 1) * TH, x0, src, tid);
-        __pipeline_commit();                             // in flight during the column pass below
+        if (k + 1 < nsteps) stage_step(y_begin + R + (k + 1) * TH);   // in flight during the column pass below
 
         // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
         const int y0 = y_begin + k * TH;
@@ -251,12 +318,12 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows) {
     }
 }
 
-template <int R, int SRC>
-cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms) {
+template <int R, int SRC, bool TMA>
+cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms, const CUtensorMap& tmap) {
     constexpr size_t smem = strip_smem_bytes<R>();
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
-        cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) configured[device] = true;
     }
@@ -272,17 +339,22 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
     if (seg_rows < 2 * STRIP_TH) seg_rows = 2 * STRIP_TH;
     const int nseg = (P.H + seg_rows - 1) / seg_rows;
     const dim3 grid(strips, nseg, frames);
-    conv_strip_kernel<R, SRC><<<grid, CONV_THREADS, smem, st>>>(P, seg_rows);
+    conv_strip_kernel<R, SRC, TMA><<<grid, CONV_THREADS, smem, st>>>(P, seg_rows, tmap);
     return cudaGetLastError();
 }
 
+// tmap: tensor map of the source plane (box = PIN columns x 32 rows x 1 frame) or nullptr -> cp.async staging
 template <int R>
-cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms) {
+cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
+                             const CUtensorMap* tmap) {
+    static const CUtensorMap none{};
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32>(P, st, device, frames, sms);
-        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32>(P, st, device, frames, sms);
-        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8>(P, st, device, frames, sms);
-        default: return launch_march_one<R, CONV_SRC_PLANE>(P, st, device, frames, sms);
+        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none);
+        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none);
+        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none);
+        default:
+            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap)
+                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none);
     }
 }
 

@@ -287,3 +287,21 @@ def test_kernels_never_write_outside_the_level_rectangles(pkg, synth, mode_name,
             assert np.all(planes[:, :, c:] == -1), "a kernel wrote into the row padding"
             assert not np.any(planes[:, :, :c] == -1), "an output pixel was never written"
             off += planes.size
+
+
+def test_reference_driver_on_the_cuda_class():
+    """examples/main.cpp = the reference's main.cpp with one include and one type name changed, built by
+    __graft_entry__.build() (linked against the serial header where /root/reference existed: then it exits 0
+    only if max |cuda - serial| == 0)."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "main_cuda")
+    if not os.path.exists(exe):
+        pytest.skip("build/main_cuda not built")
+    for n in ("64", "512"):
+        out = subprocess.run([exe, n], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert float(out.stdout.splitlines()[0]) > 0.0                     # mean ms per GenerateDoG(), as main.cpp:74 prints
+        if "max |cuda - serial header|" in out.stdout:
+            assert "max |cuda - serial header| = 0" in out.stdout

@@ -122,3 +122,29 @@ def test_band_rows(pkg, h, octs, world):
     assert pos == h
     live = [r for _, r in spans if r]
     assert max(live) - min(live) <= align + h % align
+
+
+def test_reference_side_binding_compiles_as_cxx14(pkg, tmp_path):
+    """include/GaussDePyramid-CUDA.h is what a maintainer drops next to the reference's variant headers: it must
+    compile as C++14 with plain g++ (no CUDA headers), alone and next to the reference's own header, and link
+    against libsspyr.so only."""
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "probe.cpp"
+    ref = "/root/reference/GuassDePyramid.h"
+    src.write_text(('#include "GuassDePyramid.h"\n' if os.path.exists(ref) else "") + """
+#include "GaussDePyramid-CUDA.h"
+int main() {
+    int row[4] = {1, 2, 3, 4};
+    int* img[4] = {row, row, row, row};
+    try { GaussPyramid_cuda g(img, 4, 2); g.GenerateDoG(); g.GenerateDoG_nomp_dynamic(); return g.GaussPy[0][0][0][0] != 0; }
+    catch (const std::exception&) { return 42; }     // no GPU here: sspyr_create reports it, the class throws
+}
+""")
+    cmd = ["/usr/bin/g++", "-std=gnu++14", "-Wall", "-I", inc, str(src), "-L", os.path.dirname(pkg._lib.LIB_PATH), "-lsspyr",
+           "-Wl,-rpath," + os.path.dirname(pkg._lib.LIB_PATH), "-o", str(tmp_path / "probe")]
+    if os.path.exists(ref):
+        cmd[1:1] = ["-I/root/reference"]
+    subprocess.run(cmd, check=True)
+    import torch
+    rc = subprocess.run([str(tmp_path / "probe")]).returncode
+    assert rc == (0 if torch.cuda.is_available() else 42)
