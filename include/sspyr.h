@@ -179,7 +179,7 @@ SSPYR_API int sspyr_host_free(void* ptr);
 SSPYR_API int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* dst, int capacity);
 /* CONV mode: taps of level s (2R+1 floats, centre at R); returns R through *radius. */
 SSPYR_API int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* radius);
-/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing","conv_tall","conv_streams","conv_pipe","conv_march","conv_graph","conv_tma","occ","prefetch_next"}; 0 = default. */
+/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing","conv_tall","conv_streams","conv_pipe","conv_march","conv_graph","conv_tma","conv_waves","conv_seg_min","occ","prefetch_next"}; 0 = default. */
 SSPYR_API int sspyr_set_tuning(sspyr_handle h, const char* key, int value);
 
 /* ---- row-band halo exchange (CONV mode, multi-GPU): see DESIGN.md "Row bands" ----------------------- */

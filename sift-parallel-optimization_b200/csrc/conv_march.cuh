@@ -319,7 +319,8 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
 }
 
 template <int R, int SRC, bool TMA>
-cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms, const CUtensorMap& tmap) {
+cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms, const CUtensorMap& tmap,
+                             int waves, int seg_min) {
     constexpr size_t smem = strip_smem_bytes<R>();
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
@@ -331,12 +332,11 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);          // 4 CTAs of 256 threads at <= 64 registers
     const int strips = (P.W + CONV_TW - 1) / CONV_TW;
     // about `waves` co-resident waves of CTAs: vertical segments of a multiple of 32 rows, at least 64
-    const int waves = 2;
     long long segs = (long long)sms * per_sm * waves / ((long long)strips * frames);
     if (segs < 1) segs = 1;
     int seg_rows = (int)((P.H + segs - 1) / segs);
     seg_rows = (seg_rows + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
-    if (seg_rows < 2 * STRIP_TH) seg_rows = 2 * STRIP_TH;
+    if (seg_rows < seg_min) seg_rows = seg_min;
     const int nseg = (P.H + seg_rows - 1) / seg_rows;
     const dim3 grid(strips, nseg, frames);
     conv_strip_kernel<R, SRC, TMA><<<grid, CONV_THREADS, smem, st>>>(P, seg_rows, tmap);
@@ -346,15 +346,15 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
 // tmap: tensor map of the source plane (box = PIN columns x 32 rows x 1 frame) or nullptr -> cp.async staging
 template <int R>
 cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
-                             const CUtensorMap* tmap) {
+                             const CUtensorMap* tmap, int waves, int seg_min) {
     static const CUtensorMap none{};
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none);
-        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none);
-        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none);
+        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none, waves, seg_min);
+        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none, waves, seg_min);
+        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none, waves, seg_min);
         default:
-            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap)
-                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none);
+            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap, waves, seg_min)
+                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none, waves, seg_min);
     }
 }
 

@@ -58,6 +58,8 @@ struct Tuning {
     int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
     int conv_march = 1;        // CONV: marching strip kernel for radii <= 12 (0 = one-tile-per-CTA kernel everywhere)
     int conv_tma = 1;          // CONV strip kernel: TMA (cp.async.bulk.tensor) staging of interior steps
+    int conv_waves = 0;        // CONV strip kernel: CTA waves to aim for (0 = 3)
+    int conv_seg_min = 0;      // CONV strip kernel: minimum segment height in rows (0 = 32)
     int conv_graph = 1;        // CONV: replay the per-frame launch sequence as a CUDA graph from its 2nd use on
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
