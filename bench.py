@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="CONV row bands: read neighbour planes in the kernel over NVLink (CUDA IPC) or NCCL send/recv")
+    ap.add_argument("--slots", type=int, default=0, help="frame slots in the ring (0 = enough to cover 4x L2, 2..8)")
     ap.add_argument("--tune", default="", help="rows_per_thread=2,block=256,bx=0,pdl=1")
     return ap.parse_args()
 
@@ -236,7 +237,11 @@ def run_native(args) -> dict:
     # ring of frame slots: every step touches different HBM than the last few (L2 flush by rotation)
     slots = max(2, min(8, -(-(4 * L2_BYTES) // max(frame_bytes, 1)))) if rows else 0
     if args.workload == "c5":
-        slots = 2 if world == 1 else 2
+        slots = 2
+    if args.mode == "conv" and part == "batch":
+        slots = 8                                 # CONV launches one kernel per LEVEL for all slots of a batch call
+    if args.slots > 0:
+        slots = args.slots
     ss = None
     if rows:
         ss = pkg.ScaleSpace(rows, width, octs, S, mode=mode, outputs=outputs, frames=slots, device=local,
