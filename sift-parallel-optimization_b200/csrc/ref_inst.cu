@@ -14,8 +14,8 @@ cudaError_t launch_ref_prefetch(const void* img, size_t pitch_bytes, int row_byt
     return launch_prefetch(img, pitch_bytes, row_bytes, rows, st);
 }
 #endif
-cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, dim3 grid, dim3 block,
+cudaError_t SSPYR_CAT(launch_ref_nl, SSPYR_NL)(const RefParams& P, int pix, int rpt, bool walk, dim3 grid, dim3 block,
                                                cudaStream_t st, bool pdl) {
-    return launch_pix<SSPYR_NL>(P, pix, rpt, grid, block, st, pdl);
+    return launch_pix<SSPYR_NL>(P, pix, rpt, walk, grid, block, st, pdl);
 }
 }  // namespace sspyr

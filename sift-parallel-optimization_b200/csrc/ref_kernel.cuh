@@ -189,7 +189,8 @@ __device__ __forceinline__ void ref_load_rows(RefRows<NL, RPT>& q, const RefPara
 // windows are loaded once, and the loads of the NEXT row group are issued before the stores of the current one
 // (software prefetch), so after the first group no thread ever waits on DRAM with its stores unissued.  With a
 // grid that covers every row group the loop runs once.
-template <int NL, int PIX, int RPT>
+// WALK = false: one row group per thread (no prefetch registers); WALK = true: the persistent row walk.
+template <int NL, int PIX, int RPT, bool WALK>
 __global__ void __launch_bounds__(128, 4)
 ref_fused_kernel(const __grid_constant__ RefParams P) {
     // Frames are independent: let the next launch in the stream start filling SMs right away (PDL).
@@ -221,9 +222,11 @@ ref_fused_kernel(const __grid_constant__ RefParams P) {
 
         for (;;) {
             const int rn = r0 + stride;
-            const bool more = rn < P.H;
-            RefRows<NL, RPT> nxt;
-            if (more) ref_load_rows<NL, PIX, RPT>(nxt, P, img, rn, c, col1);   // prefetch before this group's stores
+            const bool more = WALK && rn < P.H;
+            RefRows<NL, WALK ? RPT : 1> nxt;
+            if constexpr (WALK) {
+                if (more) ref_load_rows<NL, PIX, RPT>(nxt, P, img, rn, c, col1);   // prefetch before this group's stores
+            }
 
             // ---- octave 0 ----------------------------------------------------------------------------------
             float* out0 = o0.base + fofs + (size_t)r0 * o0.pitch + c;
@@ -267,7 +270,7 @@ ref_fused_kernel(const __grid_constant__ RefParams P) {
                 }
             }
             if (!more) break;
-            cur = nxt;
+            if constexpr (WALK) cur = nxt;
             r0 = rn;
         }
     }
@@ -306,7 +309,7 @@ inline cudaError_t launch_prefetch(const void* img, size_t pitch_bytes, int row_
                               (unsigned long long)pitch_bytes, row_bytes, rows);
 }
 
-template <int NL, int PIX, int RPT>
+template <int NL, int PIX, int RPT, bool WALK>
 cudaError_t launch_one(const RefParams& P, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -318,23 +321,21 @@ cudaError_t launch_one(const RefParams& P, dim3 grid, dim3 block, cudaStream_t s
     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, ref_fused_kernel<NL, PIX, RPT>, P);
+    return cudaLaunchKernelEx(&cfg, ref_fused_kernel<NL, PIX, RPT, WALK>, P);
 }
 
 template <int NL, int PIX>
-cudaError_t launch_rpt(const RefParams& P, int rpt, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
-    switch (rpt) {
-        case 1: return launch_one<NL, PIX, 1>(P, grid, block, st, pdl);
-        default: return launch_one<NL, PIX, 2>(P, grid, block, st, pdl);
-    }
+cudaError_t launch_rpt(const RefParams& P, int rpt, bool walk, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
+    if (walk) return rpt == 1 ? launch_one<NL, PIX, 1, true>(P, grid, block, st, pdl) : launch_one<NL, PIX, 2, true>(P, grid, block, st, pdl);
+    return rpt == 1 ? launch_one<NL, PIX, 1, false>(P, grid, block, st, pdl) : launch_one<NL, PIX, 2, false>(P, grid, block, st, pdl);
 }
 
 template <int NL>
-cudaError_t launch_pix(const RefParams& P, int pix, int rpt, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
+cudaError_t launch_pix(const RefParams& P, int pix, int rpt, bool walk, dim3 grid, dim3 block, cudaStream_t st, bool pdl) {
     switch (pix) {
-        case SSPYR_PIXEL_I32: return launch_rpt<NL, SSPYR_PIXEL_I32>(P, rpt, grid, block, st, pdl);
-        case SSPYR_PIXEL_F32: return launch_rpt<NL, SSPYR_PIXEL_F32>(P, rpt, grid, block, st, pdl);
-        default: return launch_rpt<NL, SSPYR_PIXEL_U8>(P, rpt, grid, block, st, pdl);
+        case SSPYR_PIXEL_I32: return launch_rpt<NL, SSPYR_PIXEL_I32>(P, rpt, walk, grid, block, st, pdl);
+        case SSPYR_PIXEL_F32: return launch_rpt<NL, SSPYR_PIXEL_F32>(P, rpt, walk, grid, block, st, pdl);
+        default: return launch_rpt<NL, SSPYR_PIXEL_U8>(P, rpt, walk, grid, block, st, pdl);
     }
 }
 

@@ -4,7 +4,7 @@
 
 namespace sspyr {
 
-#define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, dim3, dim3, cudaStream_t, bool);
+#define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, bool, dim3, dim3, cudaStream_t, bool);
 SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 #undef SSPYR_DECL
 cudaError_t launch_ref_prefetch(const void* img, size_t pitch_bytes, int row_bytes, int rows, cudaStream_t st);
@@ -95,12 +95,12 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
 
         cudaError_t e;
         switch (h->nl) {
-            case 3: e = launch_ref_nl3(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
-            case 4: e = launch_ref_nl4(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
-            case 5: e = launch_ref_nl5(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
-            case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
-            case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
-            case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, grid, block, h->stream, pdl); break;
+            case 3: e = launch_ref_nl3(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 4: e = launch_ref_nl4(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 5: e = launch_ref_nl5(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
             default: return cudaErrorInvalidValue;   // S in 0..5 (create() rejects the rest for REF mode)
         }
         if (e != cudaSuccess) return e;
