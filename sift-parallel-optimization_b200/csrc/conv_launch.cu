@@ -14,7 +14,7 @@ SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 #undef SSPYR_DECL
 #define SSPYR_DECL(n)                                                                                  \
-    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int, const CUtensorMap*, int, int); \
+    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int, const CUtensorMap*, int, int, bool); \
     int march_box_cols_r##n();
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
@@ -60,9 +60,9 @@ cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cud
 }
 
 cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
-                           const CUtensorMap* tmap, int waves, int seg_min) {
+                           const CUtensorMap* tmap, int waves, int seg_min, bool pdl) {
     switch (r) {
-#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms, tmap, waves, seg_min);
+#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms, tmap, waves, seg_min, pdl);
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
 #undef SSPYR_CASE
@@ -197,6 +197,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 ++*launches;
             }
     }
+    const bool peered_any = h->peer[0].attached || h->peer[1].attached;   // wait/signal kernels sit between the levels
     // TMA staging for float-plane sources: the map covers the frames of this launch (frame = 3rd coordinate)
     CUtensorMap tmap;
     const CUtensorMap* tm = nullptr;
@@ -204,7 +205,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         make_plane_tensor_map(&tmap, static_cast<const float*>(P.src), g.pitch, g.H, count, h->frame_floats, march_box_cols(R)))
         tm = &tmap;
     cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms, tm, h->tune.conv_waves > 0 ? h->tune.conv_waves : 3,
-                                          h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32)
+                                          h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32, h->tune.pdl != 0 && !peered_any)
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered) {

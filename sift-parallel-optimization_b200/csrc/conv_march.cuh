@@ -170,6 +170,11 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     const int x0 = blockIdx.x * CONV_TW;
     const int y_begin = blockIdx.y * seg_rows;
     const size_t fz = blockIdx.z;
+    // Programmatic dependent launch along the level chain: the next level may be scheduled (and run its prologue)
+    // while this one drains; it reads nothing this kernel writes before its own griddepcontrol.wait returns, which
+    // happens only when this grid has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (y_begin >= P.H) return;
     const int y_end = min(P.H, y_begin + seg_rows);
     const int nsteps = (y_end - y_begin + TH - 1) / TH;
@@ -320,7 +325,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
 
 template <int R, int SRC, bool TMA>
 cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms, const CUtensorMap& tmap,
-                             int waves, int seg_min) {
+                             int waves, int seg_min, bool pdl) {
     constexpr size_t smem = strip_smem_bytes<R>();
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
@@ -338,23 +343,31 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
     seg_rows = (seg_rows + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
     if (seg_rows < seg_min) seg_rows = seg_min;
     const int nseg = (P.H + seg_rows - 1) / seg_rows;
-    const dim3 grid(strips, nseg, frames);
-    conv_strip_kernel<R, SRC, TMA><<<grid, CONV_THREADS, smem, st>>>(P, seg_rows, tmap);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(strips, nseg, frames);
+    cfg.blockDim = dim3(CONV_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_strip_kernel<R, SRC, TMA>, P, seg_rows, tmap);
 }
 
 // tmap: tensor map of the source plane (box = PIN columns x 32 rows x 1 frame) or nullptr -> cp.async staging
 template <int R>
 cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
-                             const CUtensorMap* tmap, int waves, int seg_min) {
+                             const CUtensorMap* tmap, int waves, int seg_min, bool pdl) {
     static const CUtensorMap none{};
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none, waves, seg_min);
-        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none, waves, seg_min);
-        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none, waves, seg_min);
+        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
+        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
+        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
         default:
-            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap, waves, seg_min)
-                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none, waves, seg_min);
+            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap, waves, seg_min, pdl)
+                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
     }
 }
 
