@@ -53,6 +53,14 @@ struct ConvParams {
     int src_pitch, dst_pitch, dec_pitch;   // elements / floats
     int H, W, dec_H, dec_W;
     int halo_rows;
+    // Peer-memory row bands, synchronisation fused into the strip kernel (null = not used):
+    const unsigned* wait_up;            // neighbour-above's progress counter: CTAs that stage its rows wait for `wait_need`
+    const unsigned* wait_dn;            // neighbour-below's
+    unsigned wait_need;
+    unsigned* signal_flag;              // this band's counter for this octave: the last CTA to finish publishes signal_value
+    unsigned signal_value;
+    unsigned* done_count;               // CTAs finished so far (self-resetting)
+    unsigned* timeout_mark;
     float taps[2 * 32 + 1];             // taps[k + R], k = -R..R
 };
 

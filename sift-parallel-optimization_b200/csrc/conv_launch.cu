@@ -183,32 +183,46 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     // radii above 12 and conv_march = 0 use the one-tile-per-CTA kernel.
     const long long tiles32 = (long long)((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + 31) / 32) * count;
     const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && tiles32 >= 6LL * sms));   // default: always
-    // Peer-memory halos: per-octave progress counters.  After level s of build b octave o publishes
-    // (b-1)*CONV_FLAG_STRIDE + s + 1; a level first waits until both neighbours have published the level whose
-    // rows it is about to read (level s-1 of its octave, or level S of the octave above for the decimated base).
-    const bool peered = h->peer[0].attached || h->peer[1].attached;
-    const unsigned epoch = (h->build_seq - 1) * CONV_FLAG_STRIDE;
-    if (peered && !(octave == 0 && level == 0)) {
-        const int wo = (level == 1 && octave > 0) ? octave - 1 : octave;
-        const unsigned need = epoch + (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;
-        for (int side = 0; side < 2; ++side)
-            if (h->peer[side].attached) {
-                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + wo, 1, need, h->d_flag);
-                ++*launches;
-            }
-    }
-    const bool peered_any = h->peer[0].attached || h->peer[1].attached;   // wait/signal kernels sit between the levels
+    const bool peered_any = h->peer[0].attached || h->peer[1].attached;
     // TMA staging for float-plane sources: the map covers the frames of this launch (frame = 3rd coordinate)
     CUtensorMap tmap;
     const CUtensorMap* tm = nullptr;
     if (march && src_kind == CONV_SRC_PLANE && h->tune.conv_tma != 0 &&
         make_plane_tensor_map(&tmap, static_cast<const float*>(P.src), g.pitch, g.H, count, h->frame_floats, march_box_cols(R)))
         tm = &tmap;
+    // Peer-memory halos: per-octave progress counters.  After level s of build b octave o publishes
+    // (b-1)*CONV_FLAG_STRIDE + s + 1; a level first waits until both neighbours have published the level whose
+    // rows it is about to read (level s-1 of its octave, or level S of the octave above for the decimated base).
+    // The strip kernel does both itself (edge CTAs wait, the last CTA signals); the tile kernel (R > 12) gets
+    // one-thread wait / signal kernels around it.
+    const bool peered = peered_any;
+    const unsigned epoch = (h->build_seq - 1) * CONV_FLAG_STRIDE;
+    const bool first_level = octave == 0 && level == 0;
+    const int wo = (level == 1 && octave > 0) ? octave - 1 : octave;
+    const unsigned need = epoch + (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;
+    const bool fused_sync = peered && march && h->tune.conv_fused_sync != 0;
+    if (fused_sync) {
+        if (!first_level) {
+            P.wait_up = h->peer[0].attached ? h->peer[0].flag + wo : nullptr;
+            P.wait_dn = h->peer[1].attached ? h->peer[1].flag + wo : nullptr;
+            P.wait_need = need;
+        }
+        P.signal_flag = h->d_flag + octave;
+        P.signal_value = epoch + (unsigned)level + 1;
+        P.done_count = h->d_flag + 32 + octave;
+        P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
+    } else if (peered && !first_level) {
+        for (int side = 0; side < 2; ++side)
+            if (h->peer[side].attached) {
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + wo, 1, need, h->d_flag);
+                ++*launches;
+            }
+    }
     cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms, tm, h->tune.conv_waves > 0 ? h->tune.conv_waves : 3,
                                           h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32, h->tune.pdl != 0 && !peered_any)
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
-    if (e == cudaSuccess && peered) {
+    if (e == cudaSuccess && peered && !fused_sync) {
         conv_signal_kernel<<<1, 1, 0, st>>>(h->d_flag + octave, epoch + (unsigned)level + 1);
         ++*launches;
         e = cudaGetLastError();

@@ -175,9 +175,30 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     // happens only when this grid has completed and flushed.
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (y_begin >= P.H) return;
+    if (y_begin >= P.H) return;                          // (never true: the grid covers exactly the segments)
     const int y_end = min(P.H, y_begin + seg_rows);
     const int nsteps = (y_end - y_begin + TH - 1) / TH;
+
+    // Fused halo synchronisation (row bands over peer memory): only the CTAs whose rows reach into a neighbour
+    // band wait for that neighbour to have published the level they read; interior CTAs start at once, so the
+    // halo latency hides behind the band's interior.
+    if (tid == 0) {
+        const bool need_up = P.wait_up && y_begin - R < 0;
+        const bool need_dn = P.wait_dn && y_begin + nsteps * TH + R > P.H;
+        for (int side = 0; side < 2; ++side) {
+            const unsigned* f = side == 0 ? (need_up ? P.wait_up : nullptr) : (need_dn ? P.wait_dn : nullptr);
+            if (!f) continue;
+            const long long t0 = clock64();
+            for (;;) {
+                unsigned v;
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v >= P.wait_need) break;
+                if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = P.wait_need; break; }
+                __nanosleep(100);
+            }
+        }
+    }
+    if (P.wait_up || P.wait_dn) __syncthreads();
 
     const unsigned char* src = static_cast<const unsigned char*>(P.src) + fz * P.src_frame_stride * elem;
     // a step may use TMA when its whole box lies inside the plane: needed columns inside [0, W), the 4-column
@@ -319,6 +340,20 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CONV_THREADS) {
             const int rr = c / (CONV_TW / 4), q = c - rr * (CONV_TW / 4);
             *reinterpret_cast<float4*>(sT + (size_t)rr * PT + 4 * q) = *reinterpret_cast<const float4*>(sT + (size_t)(TH + rr) * PT + 4 * q);
+        }
+    }
+    // Fused completion signal: the last CTA of the grid publishes "this level of this octave is written"
+    // (system-scope release after a device-scope count of finished CTAs) for the neighbours to acquire.
+    if (P.signal_flag) {
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+            if (atomicAdd(P.done_count, 1u) == total - 1) {
+                *P.done_count = 0;                       // ready for the next launch on this octave's stream
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.signal_flag), "r"(P.signal_value) : "memory");
+            }
         }
     }
 }

@@ -767,6 +767,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_march")) h->tune.conv_march = value;
     else if (!std::strcmp(key, "conv_graph")) h->tune.conv_graph = value;
     else if (!std::strcmp(key, "conv_tma")) h->tune.conv_tma = value;
+    else if (!std::strcmp(key, "conv_fused_sync")) h->tune.conv_fused_sync = value;
     else if (!std::strcmp(key, "conv_waves")) h->tune.conv_waves = value;
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);

@@ -60,6 +60,7 @@ struct Tuning {
     int conv_tma = 1;          // CONV strip kernel: TMA (cp.async.bulk.tensor) staging of interior steps
     int conv_waves = 0;        // CONV strip kernel: CTA waves to aim for (0 = 3)
     int conv_seg_min = 0;      // CONV strip kernel: minimum segment height in rows (0 = 32)
+    int conv_fused_sync = 1;   // CONV peer bands: wait/signal inside the strip kernel (0 = one-thread kernels around it)
     int conv_graph = 1;        // CONV: replay the per-frame launch sequence as a CUDA graph from its 2nd use on
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
