@@ -219,7 +219,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
             }
     }
     cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms, tm, h->tune.conv_waves > 0 ? h->tune.conv_waves : 3,
-                                          h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32, h->tune.pdl != 0 && (!peered_any || fused_sync))
+                                          h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32, h->tune.pdl != 0 && !peered_any)   // (PDL on peered launches measured slightly slower)
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {
