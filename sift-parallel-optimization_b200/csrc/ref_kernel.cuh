@@ -47,19 +47,21 @@ __device__ __forceinline__ void load_tab(float (&w)[N], const float* __restrict_
     }
 }
 
-// Row window of one output row: fh_t[row][0..7] (levels padded to 8) -> two uniform 128-bit loads.
+// Row window of one output row: fh_t[row][0..FT-1] (levels padded to FT = 8, or 16 when S+3 > 8) -> warp-uniform
+// 128-bit loads.
+template <int NL> __host__ __device__ constexpr int row_table_stride() { return NL <= 8 ? 8 : 16; }
+
 template <int NL>
 __device__ __forceinline__ void load_row_window(float (&f)[NL], const float* __restrict__ fh_t, int orow) {
-    const float4* q = reinterpret_cast<const float4*>(fh_t + (size_t)orow * 8);
-    const float4 a = __ldg(q);
-    f[0] = a.x; f[1] = a.y; f[2] = a.z;
-    if constexpr (NL > 3) f[3] = a.w;
-    if constexpr (NL > 4) {
-        const float4 b = __ldg(q + 1);
-        f[4] = b.x;
-        if constexpr (NL > 5) f[5] = b.y;
-        if constexpr (NL > 6) f[6] = b.z;
-        if constexpr (NL > 7) f[7] = b.w;
+    constexpr int FT = row_table_stride<NL>();
+    const float4* q = reinterpret_cast<const float4*>(fh_t + (size_t)orow * FT);
+#pragma unroll
+    for (int k = 0; k < (NL + 3) / 4; ++k) {
+        const float4 a = __ldg(q + k);
+        if (4 * k + 0 < NL) f[4 * k + 0] = a.x;
+        if (4 * k + 1 < NL) f[4 * k + 1] = a.y;
+        if (4 * k + 2 < NL) f[4 * k + 2] = a.z;
+        if (4 * k + 3 < NL) f[4 * k + 3] = a.w;
     }
 }
 
@@ -190,8 +192,9 @@ __device__ __forceinline__ void ref_load_rows(RefRows<NL, RPT>& q, const RefPara
 // (software prefetch), so after the first group no thread ever waits on DRAM with its stores unissued.  With a
 // grid that covers every row group the loop runs once.
 // WALK = false: one row group per thread (no prefetch registers); WALK = true: the persistent row walk.
+// (S+3 > 8 levels is the rarely used wide build: no register cap, so nothing spills)
 template <int NL, int PIX, int RPT, bool WALK>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(128, NL <= 8 ? 4 : 1)
 ref_fused_kernel(const __grid_constant__ RefParams P) {
     // Frames are independent: let the next launch in the stream start filling SMs right away (PDL).
     asm volatile("griddepcontrol.launch_dependents;");

@@ -5,7 +5,8 @@
 namespace sspyr {
 
 #define SSPYR_DECL(n) cudaError_t launch_ref_nl##n(const RefParams&, int, int, bool, dim3, dim3, cudaStream_t, bool);
-SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
+SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8) SSPYR_DECL(9) SSPYR_DECL(10)
+SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_DECL(14) SSPYR_DECL(15) SSPYR_DECL(16)
 #undef SSPYR_DECL
 cudaError_t launch_ref_prefetch(const void* img, size_t pitch_bytes, int row_bytes, int rows, cudaStream_t st);
 
@@ -101,7 +102,15 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
             case 6: e = launch_ref_nl6(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
             case 7: e = launch_ref_nl7(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
             case 8: e = launch_ref_nl8(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
-            default: return cudaErrorInvalidValue;   // S in 0..5 (create() rejects the rest for REF mode)
+            case 9: e = launch_ref_nl9(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 10: e = launch_ref_nl10(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 11: e = launch_ref_nl11(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 12: e = launch_ref_nl12(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 13: e = launch_ref_nl13(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 14: e = launch_ref_nl14(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 15: e = launch_ref_nl15(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            case 16: e = launch_ref_nl16(P, h->cfg.pixel_type, rpt, h->tune.occ > 0, grid, block, h->stream, pdl); break;
+            default: return cudaErrorInvalidValue;   // S+3 in 3..16 (create() rejects the rest)
         }
         if (e != cudaSuccess) return e;
         ++*launches;

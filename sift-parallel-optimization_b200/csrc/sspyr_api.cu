@@ -126,7 +126,6 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
     if (cfg.height < 1 || cfg.width < 1) return fail(nullptr, SSPYR_ERR_ARG, "height and width must be >= 1");
     if (cfg.S < 0 || cfg.S + 3 > SSPYR_MAX_LEVELS) return fail(nullptr, SSPYR_ERR_ARG, "S out of range");
     if (cfg.mode != SSPYR_MODE_REF && cfg.mode != SSPYR_MODE_CONV) return fail(nullptr, SSPYR_ERR_ARG, "bad mode");
-    if (cfg.mode == SSPYR_MODE_REF && cfg.S > 5) return fail(nullptr, SSPYR_ERR_UNSUPPORTED, "REF mode supports S <= 5");
     if (cfg.mode == SSPYR_MODE_CONV && cfg.S < 1) return fail(nullptr, SSPYR_ERR_ARG, "CONV mode needs S >= 1");
     if (cfg.pixel_type < 0 || cfg.pixel_type > SSPYR_PIXEL_U8) return fail(nullptr, SSPYR_ERR_ARG, "bad pixel type");
     if (cfg.frames < 1) cfg.frames = 1;
@@ -203,7 +202,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             g.fw_off = tab;
             tab += (size_t)nl * g.pitch;
             g.fh_off = tab;
-            tab += (size_t)8 * g.H;                       // transposed [H][8]
+            tab += (size_t)(nl <= 8 ? 8 : 16) * g.H;      // transposed [H][8] ([H][16] for more than 8 levels)
         }
     }
     h->frame_floats = round_up(off, 64);
@@ -220,7 +219,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
                 ref_window(cfg.width, o, s, cfg.sigma0, full.data());
                 std::memcpy(&h->h_tables[g.fw_off + (size_t)s * g.pitch], full.data(), sizeof(float) * g.W);
                 ref_window(cfg.full_height, o, s, cfg.sigma0, full.data());
-                for (int r = 0; r < g.H; ++r) h->h_tables[g.fh_off + (size_t)r * 8 + s] = full[r0 + r];
+                for (int r = 0; r < g.H; ++r) h->h_tables[g.fh_off + (size_t)r * (nl <= 8 ? 8 : 16) + s] = full[r0 + r];
             }
         }
     } else {
@@ -577,7 +576,7 @@ int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* d
     if (axis == 1) {
         CU(h, cudaMemcpy(dst, h->d_tables + g.fw_off + (size_t)level * g.pitch, sizeof(float) * n, cudaMemcpyDeviceToHost));
     } else {   // row window is stored transposed, [row][8]
-        CU(h, cudaMemcpy2D(dst, sizeof(float), h->d_tables + g.fh_off + level, 8 * sizeof(float), sizeof(float), n,
+        CU(h, cudaMemcpy2D(dst, sizeof(float), h->d_tables + g.fh_off + level, (h->nl <= 8 ? 8 : 16) * sizeof(float), sizeof(float), n,
                            cudaMemcpyDeviceToHost));
     }
     return n;

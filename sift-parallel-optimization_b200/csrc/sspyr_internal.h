@@ -29,7 +29,7 @@ struct OctGeom {
 struct RefOct {
     float* base;               // [G_0..G_{S+1} | DoG_0..DoG_{S+1} | G_{S+2}] of frame 0 of the launch
     const float* fw;           // [NL][pitch]
-    const float* fh;           // [H][8]: row window, transposed (levels padded to 8)
+    const float* fh;           // [H][8] ([H][16] when S+3 > 8): row window, transposed
     int H, W, pitch;
     unsigned long long plane;
 };

@@ -118,7 +118,7 @@ def test_window_tables_on_device_equal_the_oracle(pkg, O):
                 assert bits_equal(ss.window_table(o, s, 1), O.window(w, o, s))
 
 
-@pytest.mark.parametrize("S,sigma0", [(0, 2.0), (2, 2.0), (5, 2.0), (3, 1.6), (3, 7.5)])
+@pytest.mark.parametrize("S,sigma0", [(0, 2.0), (2, 2.0), (5, 2.0), (3, 1.6), (3, 7.5), (6, 2.0), (9, 2.0), (13, 2.0)])
 def test_scales_and_sigma(pkg, O, synth, S, sigma0):
     img = synth.noise(96, 160)
     ref = O.ref_build(img, octaves=4, S=S, sigma0=sigma0)

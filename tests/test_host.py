@@ -70,7 +70,7 @@ def test_create_rejects_bad_configs_before_touching_cuda(pkg):
 
     assert rc(height=0) == pkg._lib.ERR_ARG
     assert rc(S=-1) == pkg._lib.ERR_ARG
-    assert rc(S=9) == pkg._lib.ERR_UNSUPPORTED            # REF kernels are instantiated for S <= 5
+    assert rc(S=14) == pkg._lib.ERR_ARG                   # S + 3 levels <= SSPYR_MAX_LEVELS = 16
     assert rc(mode=7) == pkg._lib.ERR_ARG
     assert rc(octaves=8) == pkg._lib.ERR_ARG              # 64 -> at most 7 octaves (GuassDePyramid.h:48-53)
     assert rc(full_height=128, band_row0=8, octaves=5) == pkg._lib.ERR_ARG   # band not aligned to 2^(O-1)
