@@ -305,3 +305,29 @@ def test_reference_driver_on_the_cuda_class():
         assert float(out.stdout.splitlines()[0]) > 0.0                     # mean ms per GenerateDoG(), as main.cpp:74 prints
         if "max |cuda - serial header|" in out.stdout:
             assert "max |cuda - serial header| = 0" in out.stdout
+
+
+def test_pgm_ingest_example(pkg, O, synth, tmp_path):
+    """examples/pgm_pyramid.cpp: 8-bit PGM in -> u8 ingest -> levels out as PGM, through the C ABI from C++."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "build", "pgm_pyramid")
+    if not os.path.exists(exe):
+        pytest.skip("build/pgm_pyramid not built")
+    h, w = 120, 200
+    img = synth.noise(h, w).astype(np.uint8)
+    src = tmp_path / "in.pgm"
+    src.write_bytes(b"P5\n# synthetic\n%d %d\n255\n" % (w, h) + img.tobytes())
+    for mode in ("ref", "conv"):
+        out = subprocess.run([exe, str(src), str(tmp_path / mode), mode, "3"], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert f"{w}x{h}, 3 octaves x 6 levels" in out.stdout
+        for o in range(3):
+            data = (tmp_path / f"{mode}_o{o}_g0.pgm").read_bytes()
+            head = b"P5\n%d %d\n255\n" % (w >> o, h >> o)
+            assert data.startswith(head) and len(data) == len(head) + (w >> o) * (h >> o)
+    # CONV level 0 of octave 0 is a mild blur of the input: its PGM must match the specification to +-1 grey level
+    got = np.frombuffer((tmp_path / "conv_o0_g0.pgm").read_bytes()[-h * w:], dtype=np.uint8).reshape(h, w).astype(np.float32)
+    want = np.clip(O.conv_build(img.astype(np.int32), 3, 3)["gauss"][0][0] + 0.5, 0, 255).astype(np.uint8).astype(np.float32)
+    assert np.max(np.abs(got - want)) <= 1
