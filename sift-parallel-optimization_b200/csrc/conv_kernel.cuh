@@ -77,6 +77,23 @@ template <int R, int TH, int NBUF> __host__ __device__ constexpr size_t conv_sme
 
 namespace {
 
+// ---- packed fp32 (Blackwell FFMA2): two independent IEEE fma.rn per instruction -----------------------------
+// d = {a.lo*b.lo + c.lo, a.hi*b.hi + c.hi}.  Each half rounds exactly like fmaf, so results are bit-identical to
+// the scalar chains; a {w, w} multiplier built from one scalar is folded by ptxas into a broadcast operand
+// (SASS: FFMA2 Rd, Ra.F32x2.HI_LO, URw.F32, Rc.F32x2.HI_LO), i.e. the taps cost no extra registers or moves.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 template <int SRC>
 __device__ __forceinline__ float load_src(const void* __restrict__ base, size_t idx) {
     if constexpr (SRC == SSPYR_PIXEL_I32) return (float)__ldg(static_cast<const int*>(base) + idx);

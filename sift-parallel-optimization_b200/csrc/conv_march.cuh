@@ -134,9 +134,9 @@ __device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float*
 #pragma unroll
         for (int i = 0; i < CONV_PX; ++i) acc[i] = 0.0f;
 #pragma unroll
-        for (int k = 0; k <= 2 * R; ++k) {
-            const float w = P.taps[k];
-#pragma unroll
+        for (int k = 0; k <= 2 * R; ++k) {                     // taps outer: 16 independent FMA chains in flight
+            const float w = P.taps[k];                         // (packed FFMA2 here needs shifted operand pairs: the
+#pragma unroll                                                 //  extra moves and registers made it slower, measured)
             for (int i = 0; i < CONV_PX; ++i) acc[i] = fmaf(w, in[i + k + (RA - R)], acc[i]);
         }
         float4* out4 = reinterpret_cast<float4*>(sT + (T0 + row) * PT + cb * CONV_PX);
@@ -151,7 +151,7 @@ __device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float*
 // Steps that touch the frame edge (clamp-to-edge is not a TMA fill mode) or a neighbour band's halo rows keep
 // the cp.async path.
 template <int R, int SRC, bool TMA>
-__global__ void __launch_bounds__(CONV_THREADS, 3)
+__global__ void __launch_bounds__(CONV_THREADS, 4)
 conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __grid_constant__ CUtensorMap tmap) {
     static_assert(2 * R <= STRIP_TH, "the carried rows must fit above the new ones");
     constexpr int TH = STRIP_TH;
@@ -276,23 +276,25 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             }
         }
         const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
-        float acc[PY][4];
+        f32x2 a01[PY], a23[PY];                          // packed accumulators: columns (0,1) and (2,3) of each row
 #pragma unroll
-        for (int j = 0; j < PY; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.0f; }
+        for (int j = 0; j < PY; ++j) a01[j] = a23[j] = pk2(0.0f, 0.0f);
 #pragma unroll
         for (int i = 0; i < PY + 2 * R; ++i) {
             const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
+            const f32x2 v01 = pk2(v.x, v.y), v23 = pk2(v.z, v.w);
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
-                if (i - j >= 0 && i - j <= 2 * R) {
-                    const float w = P.taps[i - j];
-                    acc[j][0] = fmaf(w, v.x, acc[j][0]);
-                    acc[j][1] = fmaf(w, v.y, acc[j][1]);
-                    acc[j][2] = fmaf(w, v.z, acc[j][2]);
-                    acc[j][3] = fmaf(w, v.w, acc[j][3]);
+                if (i - j >= 0 && i - j <= 2 * R) {            // compile-time after unrolling
+                    const f32x2 w = pk2(P.taps[i - j], P.taps[i - j]);
+                    a01[j] = fma2(w, v01, a01[j]);
+                    a23[j] = fma2(w, v23, a23[j]);
                 }
             }
         }
+        float acc[PY][4];
+#pragma unroll
+        for (int j = 0; j < PY; ++j) { unpk2(a01[j], acc[j][0], acc[j][1]); unpk2(a23[j], acc[j][2], acc[j][3]); }
         if (nvalid >= 4) {                               // full quad: vector stores, one running offset
             unsigned o = (unsigned)yr * (unsigned)P.dst_pitch + (unsigned)x;   // a plane has < 2^32 floats
 #pragma unroll
