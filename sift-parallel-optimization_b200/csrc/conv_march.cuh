@@ -225,14 +225,19 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         __pipeline_commit();
     };
 
-    // warm-up: the 2R rows above the segment
-    strip_stage_rows<R, SRC, 2 * R>(P, sIn, y_begin - R, x0, src, tid);
-    __pipeline_commit();
-    __pipeline_wait_prior(0);
-    __syncthreads();
-    strip_row_pass<R, 2 * R, 0>(P, sIn, sT, tid);
-    __syncthreads();
+    // prologue: the 2R warm-up rows above the segment go to a scratch area inside sT (the rows the first step's row
+    // pass will overwrite later) while the first step's 32 rows go to sIn -- both in flight at once, one wait
+    float* scratch = sT + (size_t)(2 * R) * PT;
+    static_assert((size_t)2 * R * conv_pitch_in<R>() <= (size_t)STRIP_TH * conv_pitch_t(), "warm-up scratch must fit in sT");
+    strip_stage_rows<R, SRC, 2 * R>(P, scratch, y_begin - R, x0, src, tid);
     stage_step(y_begin + R);
+    __pipeline_wait_prior(0);
+    if (pending_tma) {
+        if (!mbar_wait(&bar, phase)) return;
+        phase ^= 1;
+    }
+    __syncthreads();
+    strip_row_pass<R, 2 * R, 0>(P, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
 
     const int cq = tid & 31, rb = tid >> 5;             // column quad / row block of the column pass
     const int x = x0 + cq * 4;
@@ -243,13 +248,15 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
 
 #pragma unroll 1
     for (int k = 0; k < nsteps; ++k) {
-        if (pending_tma) {
-            if (!mbar_wait(&bar, phase)) return;         // (bounded; never observed)
-            phase ^= 1;
-        } else {
-            __pipeline_wait_prior(0);
+        if (k > 0) {                                     // (step 0 was awaited in the prologue)
+            if (pending_tma) {
+                if (!mbar_wait(&bar, phase)) return;     // (bounded; never observed)
+                phase ^= 1;
+            } else {
+                __pipeline_wait_prior(0);
+            }
         }
-        __syncthreads();                                 // new rows landed; carried rows are in place
+        __syncthreads();                                 // new rows landed; carried rows are in place; scratch is free
         strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
         __syncthreads();
         if (k + 1 < nsteps) stage_step(y_begin + R + (k + 1) * TH);   // in flight during the column pass below
