@@ -1,4 +1,6 @@
-// csrc/conv_kernel.cuh -- CONV mode: one fused sm_100a kernel per scale-space level.
+// csrc/conv_kernel.cuh -- CONV mode: one fused sm_100a kernel per scale-space level.  This file holds the
+// shared definitions and the one-tile-per-CTA kernel (used for radii > 12 and on request); the default kernel for
+// radii <= 12 is the marching strip kernel in conv_march.cuh, which does the same arithmetic in a better schedule.
 //
 // NOT in the reference (its "GaussFilter" is a pointwise window, GuassDePyramid.h:122-131); this is the
 // separable Gaussian blur BASELINE.json's north_star describes, specified in DESIGN.md "CONV mode" and
