@@ -219,3 +219,28 @@ def test_row_bands_reading_neighbour_planes_in_place(pkg, O, synth, world):
         check(y.download_dog(), [ref["dog"][o][:, row0 >> o:(row0 >> o) + (rows >> o)] for o in range(octs)], 255.0, "dog")
         x.close()
         y.close()
+
+
+def _random_conv_geometries(seed, n):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        h, w = int(rng.integers(1, 260)), int(rng.integers(1, 600))
+        all_o = int(min(h, w)).bit_length()
+        out.append((h, w, int(rng.integers(1, min(all_o, 5) + 1)), int(rng.integers(2, 5)), float(rng.choice([3.0, 4.0])),
+                    int(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("h,w,octs,S,rs,march", _random_conv_geometries(77, 20) + [(1, 1, 1, 3, 3.0, 1), (2, 300, 2, 3, 3.0, 1),
+                                                                                     (300, 2, 2, 3, 3.0, 0), (33, 129, 3, 3, 4.0, 1)])
+def test_random_geometries_conv_within_tolerance(pkg, O, synth, h, w, octs, S, rs, march):
+    """Seeded sweep of odd shapes for both CONV kernels (planes smaller than a tile, than the blur radius, ...)."""
+    img = synth.noise(h, w, frame=h * 1000 + w)
+    ref = O.conv_build(img, octs, S, radius_sigmas=rs)
+    with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs) as ss:
+        ss.set_tuning(conv_march=march)
+        ss.upload(img)
+        ss.build()
+        check(ss.download_gauss(), ref["gauss"], 255.0, "gauss")
+        check(ss.download_dog(), ref["dog"], 255.0, "dog")

@@ -331,3 +331,28 @@ def test_pgm_ingest_example(pkg, O, synth, tmp_path):
     got = np.frombuffer((tmp_path / "conv_o0_g0.pgm").read_bytes()[-h * w:], dtype=np.uint8).reshape(h, w).astype(np.float32)
     want = np.clip(O.conv_build(img.astype(np.int32), 3, 3)["gauss"][0][0] + 0.5, 0, 255).astype(np.uint8).astype(np.float32)
     assert np.max(np.abs(got - want)) <= 1
+
+
+def _random_geometries(seed, n, max_h, max_w):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        h, w = int(rng.integers(1, max_h)), int(rng.integers(1, max_w))
+        all_o = int(min(h, w)).bit_length()
+        out.append((h, w, int(rng.integers(1, all_o + 1)), int(rng.integers(0, 6))))
+    return out
+
+
+@pytest.mark.parametrize("h,w,octs,S", _random_geometries(20261018, 24, 300, 700) + [(1, 1, 1, 3), (2, 3, 2, 0), (7, 4, 3, 2),
+                                                                                      (3, 1029, 2, 3), (1025, 3, 2, 1)])
+def test_random_geometries_ref_bit_exact(pkg, O, synth, h, w, octs, S):
+    """Seeded sweep of odd shapes (widths below one quad, heights of one row, every octave/level count)."""
+    img = synth.noise(h, w, frame=h * 1000 + w)
+    ref = O.ref_build(img, octaves=octs, S=S)
+    with pkg.ScaleSpace(h, w, octs, S) as ss:
+        ss.upload(img)
+        ss.build()
+        for o, a in enumerate(ss.download_gauss()):
+            assert bits_equal(a, ref["gauss"][o]), f"gauss octave {o}"
+        for o, a in enumerate(ss.download_inplace()):
+            assert bits_equal(a, ref["inplace"][o]), f"in-place octave {o}"
