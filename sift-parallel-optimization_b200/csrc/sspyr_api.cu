@@ -12,6 +12,14 @@ using namespace sspyr;
 
 namespace {
 
+// rows x cols floats from a pitched device plane block to a dense host block; one linear copy when the rows are
+// already contiguous (pitch == cols), which the copy engine moves a little faster than a strided 2-D copy
+cudaError_t copy_planes_to_host(float* dst, const float* src, int cols, int pitch, size_t rows, cudaStream_t st) {
+    if (pitch == cols) return cudaMemcpyAsync(dst, src, sizeof(float) * rows * cols, cudaMemcpyDeviceToHost, st);
+    return cudaMemcpy2DAsync(dst, sizeof(float) * cols, src, sizeof(float) * pitch, sizeof(float) * cols, rows,
+                             cudaMemcpyDeviceToHost, st);
+}
+
 thread_local std::string g_create_err;
 
 int fail(sspyr_ctx* h, int code, const std::string& msg) {
@@ -514,8 +522,7 @@ int sspyr_download_inplace(sspyr_handle h, int frame, float* dst) {
     for (int o = 0; o < h->octaves; ++o) {
         const OctGeom& g = h->oct[o];
         const float* src = frame_out(h, frame) + g.off + (size_t)(nl - 1) * g.plane;   // DoG_0 .. G_{S+2}
-        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, src, sizeof(float) * g.pitch, sizeof(float) * g.W,
-                                (size_t)nl * g.H, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, copy_planes_to_host(dst, src, g.W, g.pitch, (size_t)nl * g.H, h->stream));
         dst += (size_t)nl * g.H * g.W;
     }
     return SSPYR_OK;
@@ -531,11 +538,9 @@ int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
     for (int o = 0; o < h->octaves; ++o) {
         const OctGeom& g = h->oct[o];
         const float* base = frame_out(h, frame) + g.off;
-        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, base, sizeof(float) * g.pitch, sizeof(float) * g.W,
-                                (size_t)(nl - 1) * g.H, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, copy_planes_to_host(dst, base, g.W, g.pitch, (size_t)(nl - 1) * g.H, h->stream));
         dst += (size_t)(nl - 1) * g.H * g.W;
-        CU(h, cudaMemcpy2DAsync(dst, sizeof(float) * g.W, base + (size_t)(2 * nl - 2) * g.plane, sizeof(float) * g.pitch,
-                                sizeof(float) * g.W, g.H, cudaMemcpyDeviceToHost, h->stream));
+        CU(h, copy_planes_to_host(dst, base + (size_t)(2 * nl - 2) * g.plane, g.W, g.pitch, g.H, h->stream));
         dst += (size_t)g.H * g.W;
     }
     return SSPYR_OK;
