@@ -290,7 +290,7 @@ def test_kernels_never_write_outside_the_level_rectangles(pkg, synth, mode_name,
 
 
 def test_reference_driver_on_the_cuda_class():
-    """examples/main.cpp = the reference's main.cpp with one include and one type name changed, built by
+    """examples/drop_in_driver.cpp = the reference driver's call sequence on GaussPyramid_cuda, built by
     __graft_entry__.build() (linked against the serial header where /root/reference existed: then it exits 0
     only if max |cuda - serial| == 0)."""
     import os
