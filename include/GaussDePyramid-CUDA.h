@@ -110,17 +110,16 @@ public:
     void GenerateDoG_mpi(int, char**) { GenerateDoG(); }
     void GenerateDoG_mpi_normal(int, char**) { GenerateDoG(); }
 
-    // GuassDePyramid.h:89-104
+    // GuassDePyramid.h:89-104: level 0 of every octave, one text row per image row, a ruler of "==" per octave.
     void output() {
-        int len = length;
-        for (int i = 0; i < layer; ++i) {
-            for (int j = 0; j < len; ++j) {
-                for (int k = 0; k < len; ++k) std::cout << GaussPy[i][0][j][k] << " ";
+        for (int o = 0; o < layer; ++o) {
+            const int n = side(o);
+            for (int r = 0; r < n; ++r) {
+                const float* row = GaussPy[o][0][r];
+                for (int c = 0; c < n; ++c) std::cout << row[c] << " ";
                 std::cout << std::endl;
             }
-            for (int k = 0; k < len; ++k) std::cout << "==";
-            std::cout << std::endl;
-            len /= 2;
+            std::cout << std::string(2 * (size_t)n, '=') << std::endl;
         }
     }
 
