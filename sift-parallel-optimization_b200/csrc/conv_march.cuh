@@ -42,6 +42,7 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 // Bounded wait (a lost TMA must not hang the GPU): returns false on time-out.
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
     const unsigned addr = smem_u32(bar);
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 22); ++spin) {
         unsigned ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
@@ -258,30 +259,41 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         }
         __syncthreads();                                 // new rows landed; carried rows are in place; scratch is free
         strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
-        __syncthreads();
-        if (k + 1 < nsteps) stage_step(y_begin + R + (k + 1) * TH);   // in flight during the column pass below
 
-        // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
+        // ---- centre values for DoG_{s-1} = G_{s-1} - G_s: input rows yr .. yr+PY-1 of this thread's quad ----
+        // Output row y0 + m is staged row m - R of this step, so all but the first R rows of the step are still in
+        // sIn: they are read from shared memory here, BEFORE the buffer is handed to the next step's loads (a global
+        // re-read was an L2 hit whose latency the column pass could not cover: 11 % of all stall samples).  Only the
+        // warps that own the first R output rows re-read those rows from global (they were staged one step ago).
         const int y0 = y_begin + k * TH;
         const int yr = y0 + rb * PY;                     // first output row of this thread
-        // centre values for DoG (input rows yr..yr+PY-1, an L2 hit): issued first so that they land during the FMAs
         float cen[PY][4];
         if (d && nvalid >= 4) {
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
-                const unsigned char* crow = src + (size_t)min(yr + j, P.H - 1) * P.src_pitch * elem;
-                if constexpr (SRC == SSPYR_PIXEL_I32) {
-                    const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(crow) + x));
-                    cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
-                } else if constexpr (SRC == SSPYR_PIXEL_U8) {
-                    const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
-                    cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
-                } else {
-                    const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
+                const int m = rb * PY + j - R;           // staged row of this step (warp-uniform)
+                if (m >= 0) {
+                    const float4 t = *reinterpret_cast<const float4*>(sIn + (size_t)m * PIN + RA_ + cq * 4);
                     cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                } else {
+                    const unsigned char* crow = src + (size_t)min(yr + j, P.H - 1) * P.src_pitch * elem;
+                    if constexpr (SRC == SSPYR_PIXEL_I32) {
+                        const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(crow) + x));
+                        cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                    } else if constexpr (SRC == SSPYR_PIXEL_U8) {
+                        const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
+                        cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                    } else {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
+                        cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                    }
                 }
             }
         }
+        __syncthreads();
+        if (k + 1 < nsteps) stage_step(y_begin + R + (k + 1) * TH);   // in flight during the column pass below
+
+        // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
         const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
         f32x2 a01[PY], a23[PY];                          // packed accumulators: columns (0,1) and (2,3) of each row
 #pragma unroll
@@ -344,11 +356,19 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                 }
             }
         }
-        __syncthreads();                                 // every column pass has read the rows about to be replaced
-        // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH)
-        for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CONV_THREADS) {
-            const int rr = c / (CONV_TW / 4), q = c - rr * (CONV_TW / 4);
-            *reinterpret_cast<float4*>(sT + (size_t)rr * PT + 4 * q) = *reinterpret_cast<const float4*>(sT + (size_t)(TH + rr) * PT + 4 * q);
+        // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH).
+        // Only the first CW warps' column passes read the destination rows (rb*PY < 2R), so only they meet at a
+        // named barrier and do the copy; the other warps go straight on to wait for the next step's rows.  The
+        // source rows are not written before the next row pass, which every warp enters through the full barrier
+        // at the top of the loop.
+        constexpr int CW = (2 * R + PY - 1) / PY;
+        static_assert(CW * 32 <= CONV_THREADS, "carry warps");
+        if (k + 1 < nsteps && rb < CW) {
+            asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
+            for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CW * 32) {
+                const int rr = c / (CONV_TW / 4), q = c - rr * (CONV_TW / 4);
+                *reinterpret_cast<float4*>(sT + (size_t)rr * PT + 4 * q) = *reinterpret_cast<const float4*>(sT + (size_t)(TH + rr) * PT + 4 * q);
+            }
         }
     }
     // Fused completion signal: the last CTA of the grid publishes "this level of this octave is written"
