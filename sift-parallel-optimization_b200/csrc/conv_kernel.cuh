@@ -63,6 +63,13 @@ struct ConvParams {
     unsigned signal_value;
     unsigned* done_count;               // CTAs finished so far (self-resetting)
     unsigned* timeout_mark;
+    // Level chaining inside one octave (strip kernel, null = not used): every (strip, segment) CTA counts its builds
+    // in seg_pub; with seg_dep set, a CTA waits for the up to 3x3 segments of the previous level it reads instead
+    // of for the whole previous grid.
+    unsigned* seg_pub;                  // this level's counters, frame 0 of the launch: [segment][strip]
+    const unsigned* seg_dep;            // the previous level's counters (same geometry)
+    unsigned seg_frame_stride;          // counters between consecutive frame slots
+    int src_evict_first;                // strip kernel, TMA staging: load the source plane with an L2 evict-first policy
     float taps[2 * 32 + 1];             // taps[k + R], k = -R..R
 };
 

@@ -14,7 +14,7 @@ SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 #undef SSPYR_DECL
 #define SSPYR_DECL(n)                                                                                  \
-    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, int, const CUtensorMap*, int, int, bool); \
+    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, const CUtensorMap*, int, bool); \
     int march_box_cols_r##n();
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
@@ -59,10 +59,10 @@ cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cud
     }
 }
 
-cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
-                           const CUtensorMap* tmap, int waves, int seg_min, bool pdl) {
+cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
+                           const CUtensorMap* tmap, int seg_rows, bool pdl) {
     switch (r) {
-#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, sms, tmap, waves, seg_min, pdl);
+#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, tmap, seg_rows, pdl);
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
 #undef SSPYR_CASE
@@ -120,8 +120,13 @@ unsigned char* conv_halo_raw(const sspyr_ctx* h, int down) {
 }
 
 // The blur that PRODUCES (octave, level) for frame slots first..first+count-1 (contiguous, own input slots).
+// Does (level) of this handle run on the marching strip kernel?  (radius <= 12 and not disabled)
+static bool level_marches(const sspyr_ctx* h, int level) {
+    return h->conv[level].radius <= 12 && h->tune.conv_march != 0;
+}
+
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octave, int level, cudaStream_t st,
-                             int* launches) {
+                             int* launches, bool chain) {
     if (level == 0 && octave > 0) return cudaSuccess;      // written by the decimating epilogue of (octave-1, S)
     const int nl = h->nl, S = h->cfg.S;
     const OctGeom& g = h->oct[octave];
@@ -181,9 +186,28 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     // The marching strip kernel (conv_march.cuh) row-filters every input row once and measured faster at every size;
     // radii above 12 and conv_march = 0 use the one-tile-per-CTA kernel.
-    const long long tiles32 = (long long)((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + 31) / 32) * count;
-    const bool march = R <= 12 && (h->tune.conv_march > 0 || (h->tune.conv_march < 0 && tiles32 >= 6LL * sms));   // default: always
+    const bool march = level_marches(h, level);
     const bool peered_any = h->peer[0].attached || h->peer[1].attached;
+    const int seg_rows = march_seg_rows(g.H, g.W, count, sms, h->tune.conv_waves, h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32);
+    const long long ctas = (long long)((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + seg_rows - 1) / seg_rows) * count;
+    // Level chaining (whole-pyramid builds of an unbanded handle): the strip kernels of one octave count finished
+    // segments; a level whose source plane was produced by a chained strip kernel of the same octave (same grid)
+    // waits per segment instead of per grid.  The first level of a chain -- octave 0 level 0 from the raw frame,
+    // or level 1 of a later octave, whose base comes from the octave above through an event -- keeps the grid-wide
+    // dependency.
+    // Only grids of more than one wave are chained: a smaller level has no idle tail to fill, all of its CTAs run
+    // at once and finish together, and the counter handshake then only adds latency (1080p: 5 % slower).
+    if (chain && march && h->d_seg && (h->tune.conv_chain > 1 || (h->tune.conv_chain == 1 && ctas > 4LL * sms)) && !peered_any &&
+        !conv_has_up(h) && !conv_has_down(h)) {
+        unsigned* lv0 = h->d_seg + (size_t)first * h->seg_frame_stride + h->seg_off[octave];
+        P.seg_pub = lv0 + (size_t)level * h->seg_cap[octave];
+        P.seg_frame_stride = (unsigned)h->seg_frame_stride;
+        const bool src_same_octave = level >= 2 || (level == 1 && octave == 0);
+        if (src_same_octave && level_marches(h, level - 1) && h->tune.pdl != 0)
+            P.seg_dep = lv0 + (size_t)(level - 1) * h->seg_cap[octave];
+        P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
+        P.src_evict_first = h->tune.conv_l2hint != 0 && level >= 1;
+    }
     // TMA staging for float-plane sources: the map covers the frames of this launch (frame = 3rd coordinate)
     CUtensorMap tmap;
     const CUtensorMap* tm = nullptr;
@@ -211,6 +235,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         P.signal_value = epoch + (unsigned)level + 1;
         P.done_count = h->d_flag + 32 + octave;
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
+        P.src_evict_first = h->tune.conv_l2hint != 0 && level >= 1;
     } else if (peered && !first_level) {
         for (int side = 0; side < 2; ++side)
             if (h->peer[side].attached) {
@@ -218,8 +243,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 ++*launches;
             }
     }
-    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, sms, tm, h->tune.conv_waves > 0 ? h->tune.conv_waves : 3,
-                                          h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32, h->tune.pdl != 0 && !peered_any)   // (PDL on peered launches measured slightly slower)
+    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, tm, seg_rows, h->tune.pdl != 0 && !peered_any)   // (PDL on peered launches measured slightly slower)
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {
@@ -258,14 +282,14 @@ cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches) {
     if (!fork) {
         for (int o = 0; o < h->octaves; ++o)
             for (int s = 0; s < h->nl; ++s)
-                if ((e = launch_conv_step(h, first, count, o, s, h->stream, launches)) != cudaSuccess) return e;
+                if ((e = launch_conv_step(h, first, count, o, s, h->stream, launches, true)) != cudaSuccess) return e;
         return cudaSuccess;
     }
     for (int o = 0; o < h->octaves; ++o) {
         cudaStream_t st = o == 0 ? h->stream : h->aux[o - 1];
         if (o > 0 && (e = cudaStreamWaitEvent(st, h->ev_base[o - 1], 0)) != cudaSuccess) return e;   // base of octave o ready
         for (int s = 0; s < h->nl; ++s) {
-            if ((e = launch_conv_step(h, first, count, o, s, st, launches)) != cudaSuccess) return e;
+            if ((e = launch_conv_step(h, first, count, o, s, st, launches, true)) != cudaSuccess) return e;
             if (s == S && o + 1 < h->octaves && (e = cudaEventRecord(h->ev_base[o], st)) != cudaSuccess) return e;
         }
         if (o > 0) {                                            // join
@@ -286,6 +310,12 @@ void conv_drop_graphs(sspyr_ctx* h) {
 // their cross-stream events cost more host time than the small levels take on the GPU.
 cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launches) {
     const bool peered = h->peer[0].attached || h->peer[1].attached;
+    if (h->seg_dirty && h->d_seg) {          // segment counters possibly out of step: restart all of them from zero
+        conv_drop_graphs(h);
+        const cudaError_t me = cudaMemsetAsync(h->d_seg, 0, sizeof(unsigned) * h->seg_frame_stride * h->cfg.frames, h->stream);
+        if (me != cudaSuccess) return me;
+    }
+    h->seg_dirty = false;
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (h->tune.conv_graph == 0 || peered || cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess ||
         cs != cudaStreamCaptureStatusNone)

@@ -60,6 +60,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
                    "r"(smem_u32(bar)) : "memory");
 }
 
+// Same, with an L2 evict-first policy: the source plane of a level is dead once the level has read it (only the
+// halo re-reads of neighbouring CTAs follow shortly), so it should not displace the G_s rows being written, which
+// the chained next level reads back from L2.
+__device__ __forceinline__ void tma_load_3d_evict_first(void* smem_dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                                        unsigned long long* bar) {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2),
+                   "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
     return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t()) + 16;   // + mbarrier
 }
@@ -171,11 +183,55 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     const int x0 = blockIdx.x * CONV_TW;
     const int y_begin = blockIdx.y * seg_rows;
     const size_t fz = blockIdx.z;
-    // Programmatic dependent launch along the level chain: the next level may be scheduled (and run its prologue)
-    // while this one drains; it reads nothing this kernel writes before its own griddepcontrol.wait returns, which
-    // happens only when this grid has completed and flushed.
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // Programmatic dependent launch along the level chain.
+    //   * no segment counters (row bands, tile-kernel neighbours): the next level may be scheduled while this one
+    //     drains; it reads nothing this kernel writes before its own griddepcontrol.wait returns, i.e. before this
+    //     grid has completed and flushed.
+    //   * level chaining (seg_pub set): every CTA counts the builds of its (strip, segment) in seg_pub when its rows
+    //     are written.  A level with seg_dep does NOT wait for the previous grid: each CTA waits only for the up to
+    //     3x3 segments of the previous level that its tile + halo reads, so consecutive levels overlap (no idle
+    //     tail between them, and the rows just written are still in L2).  The first level of a chain keeps the
+    //     grid-wide wait and lets its dependents go only AFTER it: a chained CTA can then never run before the
+    //     previous build of these planes has completed (own counter final, nobody still reading what it overwrites).
+    //     Dependents are scheduled only once every CTA of this grid has started, so a waiting CTA's producers are
+    //     always resident or done: no deadlock.
+    unsigned seg_next = 0;
+    const size_t seg_idx = fz * P.seg_frame_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    if (P.seg_dep) {
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (tid < 32) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seg_next) : "l"(P.seg_pub + seg_idx) : "memory");
+            seg_next += 1;
+            if (tid < 9) {
+                const int sx = (int)blockIdx.x + tid % 3 - 1, sy = (int)blockIdx.y + tid / 3 - 1;
+                if (sx >= 0 && sx < (int)gridDim.x && sy >= 0 && sy < (int)gridDim.y) {
+                    const unsigned* f = P.seg_dep + fz * P.seg_frame_stride + (size_t)sy * gridDim.x + sx;
+                    const long long t0 = clock64();
+                    for (;;) {
+                        unsigned v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                        if ((int)(v - seg_next) >= 0) break;
+                        if (*reinterpret_cast<volatile unsigned*>(P.timeout_mark) != 0) break;     // someone gave up: do not pile up waits
+                        if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = seg_next | 0x80000000u; break; }
+                        __nanosleep(64);
+                    }
+                }
+            }
+            __syncwarp();
+            if (tid == 0) asm volatile("fence.proxy.async.global;" ::: "memory");   // the TMA loads below read those rows
+        }
+        __syncthreads();
+    } else if (P.seg_pub) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;");
+        if (tid == 0) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seg_next) : "l"(P.seg_pub + seg_idx) : "memory");
+            seg_next += 1;
+        }
+    } else {
+        asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (y_begin >= P.H) return;                          // (never true: the grid covers exactly the segments)
     const int y_end = min(P.H, y_begin + seg_rows);
     const int nsteps = (y_end - y_begin + TH - 1) / TH;
@@ -216,7 +272,8 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             if (tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic reads of sIn are done
                 mbar_expect_tx(&bar, (unsigned)(TH * PIN * sizeof(float)));
-                tma_load_3d(sIn, &tmap, x0 - RA_, gy0, (int)fz, &bar);
+                if (P.src_evict_first) tma_load_3d_evict_first(sIn, &tmap, x0 - RA_, gy0, (int)fz, &bar);
+                else tma_load_3d(sIn, &tmap, x0 - RA_, gy0, (int)fz, &bar);
             }
             pending_tma = true;
         } else {
@@ -371,6 +428,15 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             }
         }
     }
+    // Level chaining: this (strip, segment) is written -- count the build for the next level's CTAs.
+    if (P.seg_pub) {
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("fence.proxy.async.global;" ::: "memory");
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.seg_pub + seg_idx), "r"(seg_next) : "memory");
+        }
+    }
     // Fused completion signal: the last CTA of the grid publishes "this level of this octave is written"
     // (system-scope release after a device-scope count of finished CTAs) for the neighbours to acquire.
     if (P.signal_flag) {
@@ -387,25 +453,40 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     }
 }
 
+// Vertical segmentation of a level for the strip kernel: about `waves` co-resident waves of CTAs (4 per SM for every
+// radius <= 12), segments of a multiple of 32 rows, at least seg_min.  Depends on the plane geometry only, so all
+// levels of an octave get the same (strip, segment) grid -- which the level chaining relies on.
+// waves <= 0: automatic -- 3 waves, but segments of at least `long_rows` rows (8 steps: the 2R warm-up rows and the
+// exposed first load are paid once per segment) as long as that still leaves 1.5 waves; measured on 8K: 5-step
+// segments x 2.7 waves 0.683 ms, 8-step x 1.7 waves 0.668 ms, 4-step x 3.4 waves 0.734 ms per pyramid.
+inline int march_seg_rows(int H, int W, int frames, int sms, int waves, int seg_min, int long_rows = 8 * STRIP_TH) {
+    const long long strips = (long long)((W + CONV_TW - 1) / CONV_TW) * frames;
+    auto rows_for = [&](long long ctas) {
+        long long segs = ctas / strips;
+        if (segs < 1) segs = 1;
+        const int r = (int)((H + segs - 1) / segs);
+        return (r + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
+    };
+    int seg_rows = rows_for((long long)sms * 4 * (waves > 0 ? waves : 3));
+    if (waves <= 0 && seg_rows < long_rows) {
+        const long long ctas_long = strips * ((H + long_rows - 1) / long_rows);
+        if (2 * ctas_long >= 3LL * sms * 4) seg_rows = long_rows;
+    }
+    return seg_rows < seg_min ? seg_min : seg_rows;
+}
+
 template <int R, int SRC, bool TMA>
-cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, int sms, const CUtensorMap& tmap,
-                             int waves, int seg_min, bool pdl) {
+cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, const CUtensorMap& tmap,
+                             int seg_rows, bool pdl) {
     constexpr size_t smem = strip_smem_bytes<R>();
+    static_assert(smem + 1024 <= (227 * 1024) / 4, "4 CTAs per SM");
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         if (device >= 0 && device < 64) configured[device] = true;
     }
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);          // 4 CTAs of 256 threads at <= 64 registers
     const int strips = (P.W + CONV_TW - 1) / CONV_TW;
-    // about `waves` co-resident waves of CTAs: vertical segments of a multiple of 32 rows, at least 64
-    long long segs = (long long)sms * per_sm * waves / ((long long)strips * frames);
-    if (segs < 1) segs = 1;
-    int seg_rows = (int)((P.H + segs - 1) / segs);
-    seg_rows = (seg_rows + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
-    if (seg_rows < seg_min) seg_rows = seg_min;
     const int nseg = (P.H + seg_rows - 1) / seg_rows;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(strips, nseg, frames);
@@ -422,16 +503,16 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
 
 // tmap: tensor map of the source plane (box = PIN columns x 32 rows x 1 frame) or nullptr -> cp.async staging
 template <int R>
-cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames, int sms,
-                             const CUtensorMap* tmap, int waves, int seg_min, bool pdl) {
+cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
+                             const CUtensorMap* tmap, int seg_rows, bool pdl) {
     static const CUtensorMap none{};
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
-        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
-        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
+        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, none, seg_rows, pdl);
+        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, none, seg_rows, pdl);
+        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, none, seg_rows, pdl);
         default:
-            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, sms, *tmap, waves, seg_min, pdl)
-                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, sms, none, waves, seg_min, pdl);
+            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, *tmap, seg_rows, pdl)
+                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, none, seg_rows, pdl);
     }
 }
 

@@ -274,6 +274,21 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (halo): ") + cudaGetErrorString(e));
         }
     }
+    if (cfg.mode == SSPYR_MODE_CONV && !banded) {           // level-chaining counters (conv_march.cuh)
+        size_t n = 0;
+        for (int o = 0; o < h->octaves; ++o) {
+            h->seg_off[o] = n;
+            h->seg_cap[o] = (size_t)((h->oct[o].W + 127) / 128) * (size_t)((h->oct[o].H + 31) / 32);
+            n += h->seg_cap[o] * nl;
+        }
+        h->seg_frame_stride = n;
+        const size_t bytes = sizeof(unsigned) * n * cfg.frames;
+        if (n * cfg.frames < (1ull << 31) &&
+            ((e = dmalloc((void**)&h->d_seg, bytes)) != cudaSuccess || (e = cudaMemset(h->d_seg, 0, bytes)) != cudaSuccess)) {
+            cudaGetLastError();
+            return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (segment counters): ") + cudaGetErrorString(e));
+        }
+    }
     if (cfg.outputs & SSPYR_OUT_EXTREMA) {
         if ((e = dmalloc((void**)&h->d_ext, h->ext_frame_bytes * cfg.frames)) != cudaSuccess) {
             cudaGetLastError();
@@ -315,6 +330,7 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
+    if (h->d_seg) cudaFree(h->d_seg);
     conv_drop_graphs(h);
     for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
@@ -423,7 +439,10 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
         for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
             e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
     }
-    if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
+    if (e != cudaSuccess) {
+        h->seg_dirty = true;                                 // some levels may have counted this build, others not
+        return fail_cuda(h, e, "kernel launch");
+    }
     if (h->tune.timing) CU(h, cudaEventRecord(h->ev1, h->stream));
     h->timed = h->tune.timing != 0;
     h->last_launches = launches;
@@ -457,10 +476,14 @@ int sspyr_sync(sspyr_handle h) {
     if (!h) return SSPYR_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (h->peer[0].attached || h->peer[1].attached) {
+    if (h->peer[0].attached || h->peer[1].attached || (h->d_seg && h->tune.conv_chain != 0)) {
         unsigned mark = 0;
         CU(h, cudaMemcpy(&mark, h->d_flag + 16, sizeof(mark), cudaMemcpyDeviceToHost));
-        if (mark) return fail(h, SSPYR_ERR_STATE, "timed out waiting for a neighbour band (counter value " + std::to_string(mark) + ")");
+        if (mark) {
+            h->seg_dirty = true;
+            CU(h, cudaMemset(h->d_flag + 16, 0, sizeof(mark)));
+            return fail(h, SSPYR_ERR_STATE, "timed out waiting for a neighbour band or a previous level (counter value " + std::to_string(mark & 0x7fffffffu) + ")");
+        }
     }
     return SSPYR_OK;
 }
@@ -758,6 +781,7 @@ int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
 int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     if (!h || !key) return SSPYR_ERR_ARG;
     conv_drop_graphs(h);
+    h->seg_dirty = true;                                     // the segment geometry of the next build may differ
     if (!std::strcmp(key, "rows_per_thread")) h->tune.rows_per_thread = value;
     else if (!std::strcmp(key, "block")) h->tune.block = value;
     else if (!std::strcmp(key, "bx")) h->tune.bx = value;
@@ -774,6 +798,8 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_fused_sync")) h->tune.conv_fused_sync = value;
     else if (!std::strcmp(key, "conv_waves")) h->tune.conv_waves = value;
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
+    else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
+    else if (!std::strcmp(key, "conv_l2hint")) h->tune.conv_l2hint = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
     return SSPYR_OK;
 }

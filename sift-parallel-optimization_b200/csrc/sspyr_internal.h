@@ -58,11 +58,17 @@ struct Tuning {
     int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
     int conv_march = 1;        // CONV: marching strip kernel for radii <= 12 (0 = one-tile-per-CTA kernel everywhere)
     int conv_tma = 1;          // CONV strip kernel: TMA (cp.async.bulk.tensor) staging of interior steps
-    int conv_waves = 0;        // CONV strip kernel: CTA waves to aim for (0 = 3)
+    int conv_waves = 0;        // CONV strip kernel: CTA waves to aim for (0 = automatic: 3, or 8-step segments, see march_seg_rows)
+    int conv_l2hint = 0;       // CONV chained levels: TMA-load the (dead after this level) source plane with L2 evict-first
+                               // (measured SLOWER -- 8K 0.679 vs 0.667 ms, 16K 5.02 vs 4.68 ms: the halo re-reads of the
+                               // neighbouring CTAs then miss -- so it is off)
     int conv_seg_min = 0;      // CONV strip kernel: minimum segment height in rows (0 = 32)
     int conv_fused_sync = 1;   // CONV peer bands: wait/signal inside the strip kernel (0 = one-thread kernels around it)
     int conv_graph = 1;        // CONV: replay the per-frame launch sequence as a CUDA graph from its 2nd use on
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
+    int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
+                               // as the segments of the previous level it reads are published (per-segment counters),
+                               // instead of after the whole previous grid (0 = grid-wide dependency only)
     int timing = 0;            // bracket every build with CUDA events (sspyr_elapsed_ms); events between two
                                // launches stop them from overlapping, so this is off unless asked for
 };
@@ -112,6 +118,12 @@ struct sspyr_ctx {
         size_t frame_floats = 0, in_frame_bytes = 0;
     } peer[2];                                   // [0] = band above, [1] = band below
     unsigned* d_flag = nullptr;                  // per-octave progress counters + timeout marker (inside d_out's allocation)
+    // CONV level chaining: one build counter per (frame slot, octave, level, segment of a strip), see conv_march.cuh
+    unsigned* d_seg = nullptr;
+    size_t seg_frame_stride = 0;                 // counters per frame slot
+    size_t seg_off[SSPYR_MAX_OCTAVES] = {0};     // first counter of an octave inside a slot
+    size_t seg_cap[SSPYR_MAX_OCTAVES] = {0};     // counters per level of that octave (strips x ceil(H/32))
+    bool seg_dirty = false;                      // counters may be out of step (tuning changed, failed build): zero them first
     unsigned build_seq = 0;                      // builds started so far (all bands issue the same sequence)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     struct GraphEntry { int first, count, seen, launches; cudaGraphExec_t exec; };
@@ -134,7 +146,7 @@ cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches);
 cudaError_t launch_conv_graphed(sspyr_ctx* h, int first_frame, int count, int* launches);
 void conv_drop_graphs(sspyr_ctx* h);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,
-                             int* launches);
+                             int* launches, bool chain = false);
 bool conv_has_up(const sspyr_ctx* h);
 bool conv_has_down(const sspyr_ctx* h);
 float* conv_halo_plane(const sspyr_ctx* h, int octave, int down);

@@ -244,3 +244,58 @@ def test_random_geometries_conv_within_tolerance(pkg, O, synth, h, w, octs, S, r
         ss.build()
         check(ss.download_gauss(), ref["gauss"], 255.0, "gauss")
         check(ss.download_dog(), ref["dog"], 255.0, "dog")
+
+
+def _all_planes(ss, frame=0):
+    return ss.download_gauss(frame) + ss.download_dog(frame)
+
+
+@pytest.mark.parametrize("h,w,octs,S,rs,frames", [(270, 480, 4, 3, 3.0, 1), (333, 1241, 3, 3, 3.0, 2), (600, 700, 3, 2, 4.0, 1),
+                                                  (97, 513, 2, 3, 3.0, 3), (2160, 3840, 3, 3, 3.0, 1)])
+def test_level_chaining_is_bit_identical(pkg, synth, h, w, octs, S, rs, frames):
+    """Level chaining (a level's CTA waits for the segments of the previous level it reads, not for the whole
+    previous grid; conv_march.cuh) is a schedule, not arithmetic: forced on (conv_chain=2, also for grids of less
+    than a wave), automatic (1) and off (0) give the same bits, build after build, with new pixels every build
+    (a CTA that ran ahead of its producer would blur the previous build's rows)."""
+    imgs = [[synth.noise(h, w, frame=10 * b + f) for f in range(frames)] for b in range(3)]
+    out = {}
+    for chain in (0, 1, 2):
+        with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=frames) as ss:
+            ss.set_tuning(conv_chain=chain)
+            got = []
+            for b in range(3):
+                for f in range(frames):
+                    ss.upload(imgs[b][f], frame=f)
+                ss.build_batch(0, frames)
+                ss.sync()
+                got.append([_all_planes(ss, f) for f in range(frames)])
+            out[chain] = got
+    for chain in (1, 2):
+        for b in range(3):
+            for f in range(frames):
+                for a, c in zip(out[0][b][f], out[chain][b][f]):
+                    np.testing.assert_array_equal(a, c)
+
+
+def test_level_chaining_survives_retuning_and_graph_replay(pkg, O, synth):
+    """The per-segment build counters restart from zero when the segmentation may change (sspyr_set_tuning), and
+    a captured launch sequence (CUDA graph, from the 2nd build of a slot on) replays them correctly."""
+    h, w, octs = 500, 900, 3
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=2) as ss:
+        ss.set_tuning(conv_chain=2)
+        for b in range(5):                                   # eager, capture, replays; alternating slots
+            img = synth.noise(h, w, frame=b)
+            ss.upload(img, frame=b % 2)
+            ss.build(b % 2)
+            if b in (0, 3, 4):
+                check(ss.download_gauss(b % 2), O.conv_build(img, octs, 3)["gauss"], 255.0, f"build {b}")
+        for waves, seg in ((2, 64), (5, 32), (0, 0)):        # new segment grids on the same handle
+            ss.set_tuning(conv_waves=waves)
+            ss.set_tuning(conv_seg_min=seg)
+            for b in range(3):
+                img = synth.noise(h, w, frame=100 + b)
+                ss.upload(img, frame=0)
+                ss.build(0)
+            ref = O.conv_build(img, octs, 3)
+            check(ss.download_gauss(0), ref["gauss"], 255.0, f"waves {waves}")
+            check(ss.download_dog(0), ref["dog"], 255.0, f"waves {waves}")
