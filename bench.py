@@ -240,6 +240,8 @@ def run_native(args) -> dict:
         slots = 2
     if args.mode == "conv" and part == "batch":
         slots = 8                                 # CONV launches one kernel per LEVEL for all slots of a batch call
+    if args.mode == "conv" and part == "replica":
+        slots = 8                                 # CONV keeps up to 8 single-frame builds in flight (frame lanes)
     if args.slots > 0:
         slots = args.slots
     ss = None
@@ -307,6 +309,11 @@ def run_native(args) -> dict:
     # launches keep consecutive frames from overlapping, so this is the isolated-step figure, not the throughput.
     per_step = None
     if ss is not None:
+        if args.mode == "conv":                  # one build at a time: no frame lanes for the isolated-step figure
+            ss.set_tuning(conv_lanes=1)
+            for _ in range(2 * slots + 2):       # (retuning drops the captured launch sequences: warm them up again)
+                step()
+            torch.cuda.synchronize()
         n_ev = max(5, min(50, steps))
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_ev)]
         for a, b in evs:
@@ -352,6 +359,8 @@ def run_native(args) -> dict:
                    "outputs": "S+3 Gaussian + S+2 DoG planes (B_full)" if args.outputs == "all"
                    else "reference in-place layout: S+2 DoG + top Gaussian (B_ref)",
                    "partition": part if world > 1 else "single GPU", "frame_slots": slots,
+                   **({"frames_in_flight": "up to %d single-frame builds overlap (frame lanes, one stream set each)" % min(8, slots)}
+                      if args.mode == "conv" and part == "replica" else {}),
                    "l2": f"ring of {slots} frame slots = {slots * frame_bytes / 1e6:.0f} MB > {L2_BYTES >> 20} MB L2; "
                          "consecutive steps touch different HBM"},
         "gpu_launches": int(dist.sum(my_launches)),

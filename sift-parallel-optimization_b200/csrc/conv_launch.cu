@@ -274,27 +274,27 @@ cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches) {
 // host can exchange halos between steps).  Octaves run concurrently: octave o+1 only depends on level S of octave o
 // (its decimated base), so each octave gets its own stream, forked from the handle's stream by events and joined
 // back at the end -- the small octaves' short kernels hide behind the large ones instead of queueing after them.
-cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches) {
+cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches, const ConvStreams& cs) {
     const int S = h->cfg.S;
-    if (conv_begin_build(h, h->stream, launches) != cudaSuccess) return cudaGetLastError();
-    const bool fork = h->tune.conv_streams != 0 && h->octaves > 1 && !h->aux.empty();
+    if (conv_begin_build(h, cs.main, launches) != cudaSuccess) return cudaGetLastError();
+    const bool fork = h->tune.conv_streams != 0 && h->octaves > 1 && cs.aux != nullptr;
     cudaError_t e;
     if (!fork) {
         for (int o = 0; o < h->octaves; ++o)
             for (int s = 0; s < h->nl; ++s)
-                if ((e = launch_conv_step(h, first, count, o, s, h->stream, launches, true)) != cudaSuccess) return e;
+                if ((e = launch_conv_step(h, first, count, o, s, cs.main, launches, true)) != cudaSuccess) return e;
         return cudaSuccess;
     }
     for (int o = 0; o < h->octaves; ++o) {
-        cudaStream_t st = o == 0 ? h->stream : h->aux[o - 1];
-        if (o > 0 && (e = cudaStreamWaitEvent(st, h->ev_base[o - 1], 0)) != cudaSuccess) return e;   // base of octave o ready
+        cudaStream_t st = o == 0 ? cs.main : cs.aux[o - 1];
+        if (o > 0 && (e = cudaStreamWaitEvent(st, cs.ev_base[o - 1], 0)) != cudaSuccess) return e;   // base of octave o ready
         for (int s = 0; s < h->nl; ++s) {
             if ((e = launch_conv_step(h, first, count, o, s, st, launches, true)) != cudaSuccess) return e;
-            if (s == S && o + 1 < h->octaves && (e = cudaEventRecord(h->ev_base[o], st)) != cudaSuccess) return e;
+            if (s == S && o + 1 < h->octaves && (e = cudaEventRecord(cs.ev_base[o], st)) != cudaSuccess) return e;
         }
         if (o > 0) {                                            // join
-            if ((e = cudaEventRecord(h->ev_done[o - 1], st)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(h->stream, h->ev_done[o - 1], 0)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(cs.ev_done[o - 1], st)) != cudaSuccess) return e;
+            if ((e = cudaStreamWaitEvent(cs.main, cs.ev_done[o - 1], 0)) != cudaSuccess) return e;
         }
     }
     return cudaSuccess;
@@ -308,18 +308,19 @@ void conv_drop_graphs(sspyr_ctx* h) {
 
 // launch_conv, replayed as a CUDA graph from the second build of the same slots on: 26+ small launches and
 // their cross-stream events cost more host time than the small levels take on the GPU.
-cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launches) {
+cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launches, const ConvStreams& cs) {
     const bool peered = h->peer[0].attached || h->peer[1].attached;
     if (h->seg_dirty && h->d_seg) {          // segment counters possibly out of step: restart all of them from zero
-        conv_drop_graphs(h);
-        const cudaError_t me = cudaMemsetAsync(h->d_seg, 0, sizeof(unsigned) * h->seg_frame_stride * h->cfg.frames, h->stream);
+        conv_drop_graphs(h);                 // (rare: after sspyr_set_tuning or a failed build; every lane has been
+        cudaError_t me = cudaStreamSynchronize(h->stream);   //  joined into the handle's stream, so this drains them all)
+        if (me == cudaSuccess) me = cudaMemset(h->d_seg, 0, sizeof(unsigned) * h->seg_frame_stride * h->cfg.frames);
         if (me != cudaSuccess) return me;
     }
     h->seg_dirty = false;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (h->tune.conv_graph == 0 || peered || cudaStreamIsCapturing(h->stream, &cs) != cudaSuccess ||
-        cs != cudaStreamCaptureStatusNone)
-        return launch_conv(h, first, count, launches);
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (h->tune.conv_graph == 0 || peered || cudaStreamIsCapturing(cs.main, &st) != cudaSuccess ||
+        st != cudaStreamCaptureStatusNone)
+        return launch_conv(h, first, count, launches, cs);
     sspyr_ctx::GraphEntry* ge = nullptr;
     for (auto& g : h->graphs)
         if (g.first == first && g.count == count) ge = &g;
@@ -329,20 +330,20 @@ cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launche
     }
     if (ge->exec) {
         *launches += ge->launches;
-        return cudaGraphLaunch(ge->exec, h->stream);
+        return cudaGraphLaunch(ge->exec, cs.main);
     }
-    if (ge->seen++ == 0) return launch_conv(h, first, count, launches);      // first use: eager (sets kernel attributes)
-    cudaError_t e = cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal);
-    if (e != cudaSuccess) { cudaGetLastError(); return launch_conv(h, first, count, launches); }
+    if (ge->seen++ == 0) return launch_conv(h, first, count, launches, cs);      // first use: eager (sets kernel attributes)
+    cudaError_t e = cudaStreamBeginCapture(cs.main, cudaStreamCaptureModeThreadLocal);
+    if (e != cudaSuccess) { cudaGetLastError(); return launch_conv(h, first, count, launches, cs); }
     int n = 0;
-    const cudaError_t le = launch_conv(h, first, count, &n);
+    const cudaError_t le = launch_conv(h, first, count, &n, cs);
     cudaGraph_t graph = nullptr;
-    e = cudaStreamEndCapture(h->stream, &graph);
+    e = cudaStreamEndCapture(cs.main, &graph);
     if (le != cudaSuccess || e != cudaSuccess || !graph) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
         h->tune.conv_graph = 0;                                              // do not try again on this handle
-        return launch_conv(h, first, count, launches);
+        return launch_conv(h, first, count, launches, cs);
     }
     e = cudaGraphInstantiate(&ge->exec, graph, 0);
     cudaGraphDestroy(graph);
@@ -350,11 +351,11 @@ cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launche
         ge->exec = nullptr;
         cudaGetLastError();
         h->tune.conv_graph = 0;
-        return launch_conv(h, first, count, launches);
+        return launch_conv(h, first, count, launches, cs);
     }
     ge->launches = n;
     *launches += n;
-    return cudaGraphLaunch(ge->exec, h->stream);
+    return cudaGraphLaunch(ge->exec, cs.main);
 }
 
 cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches) {

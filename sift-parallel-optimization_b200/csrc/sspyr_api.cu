@@ -106,6 +106,85 @@ int plane_lookup(sspyr_ctx* h, int octave, int level, int kind, int* index) {
     return SSPYR_OK;
 }
 
+// ---- CONV frame lanes (sspyr_internal.h) ---------------------------------------------------------------
+ConvStreams own_streams(sspyr_ctx* h) {
+    return ConvStreams{h->stream, h->aux.empty() ? nullptr : h->aux.data(), h->ev_base.data(), h->ev_done.data()};
+}
+
+// A library operation that later builds must follow was enqueued on the handle's stream.
+cudaError_t mark_tail(sspyr_ctx* h) {
+    if (!h->ev_tail) return cudaSuccess;
+    ++h->tail_seq;
+    return cudaEventRecord(h->ev_tail, h->stream);
+}
+
+int lane_count(const sspyr_ctx* h) {
+    if (h->cfg.mode != SSPYR_MODE_CONV || h->cfg.full_height != h->cfg.height || h->tune.timing) return 1;
+    if (h->peer[0].attached || h->peer[1].attached) return 1;
+    int n = h->tune.conv_lanes < h->cfg.frames ? h->tune.conv_lanes : h->cfg.frames;
+    return n < 1 ? 1 : (n > 16 ? 16 : n);
+}
+
+cudaError_t ensure_lanes(sspyr_ctx* h, int n) {
+    cudaError_t e;
+    if (!h->ev_tail && (e = cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if (h->slot_lane.empty()) h->slot_lane.assign(h->cfg.frames, -1);
+    while ((int)h->lanes.size() < n) {
+        h->lanes.emplace_back();
+        sspyr_ctx::Lane& L = h->lanes.back();
+        if ((e = cudaStreamCreateWithFlags(&L.main, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&L.done, cudaEventDisableTiming)) != cudaSuccess)
+            return e;
+        const int na = h->octaves - 1;
+        L.aux.assign(na, nullptr);
+        L.ev_base.assign(na, nullptr);
+        L.ev_done.assign(na, nullptr);
+        for (int o = 0; o < na; ++o)
+            if ((e = cudaStreamCreateWithFlags(&L.aux[o], cudaStreamNonBlocking)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&L.ev_base[o], cudaEventDisableTiming)) != cudaSuccess ||
+                (e = cudaEventCreateWithFlags(&L.ev_done[o], cudaEventDisableTiming)) != cudaSuccess)
+                return e;
+    }
+    return cudaSuccess;
+}
+
+void destroy_lanes(sspyr_ctx* h) {
+    for (auto& L : h->lanes) {
+        if (L.main) cudaStreamDestroy(L.main);
+        if (L.done) cudaEventDestroy(L.done);
+        for (cudaStream_t st : L.aux) if (st) cudaStreamDestroy(st);
+        for (cudaEvent_t ev : L.ev_base) if (ev) cudaEventDestroy(ev);
+        for (cudaEvent_t ev : L.ev_done) if (ev) cudaEventDestroy(ev);
+    }
+    h->lanes.clear();
+    if (h->ev_tail) cudaEventDestroy(h->ev_tail);
+    h->ev_tail = nullptr;
+}
+
+// Whole-pyramid CONV build of slots first..first+count-1 on lane (first % lanes), joined into the handle's stream.
+cudaError_t build_on_lane(sspyr_ctx* h, int first, int count, int nlanes, int* launches) {
+    cudaError_t e = ensure_lanes(h, nlanes);
+    if (e != cudaSuccess) return e;
+    const int li = first % nlanes;
+    sspyr_ctx::Lane& L = h->lanes[li];
+    if (h->strict_order && (e = mark_tail(h)) != cudaSuccess) return e;        // follow everything on the stream
+    if (L.seen_tail != h->tail_seq) {
+        if ((e = cudaStreamWaitEvent(L.main, h->ev_tail, 0)) != cudaSuccess) return e;
+        L.seen_tail = h->tail_seq;
+    }
+    for (int f = first; f < first + count; ++f) {                               // slots last written through another lane
+        const int k = h->slot_lane[f];
+        if (k >= 0 && k != li && k < (int)h->lanes.size() &&
+            (e = cudaStreamWaitEvent(L.main, h->lanes[k].done, 0)) != cudaSuccess)
+            return e;
+        h->slot_lane[f] = li;
+    }
+    const ConvStreams cs{L.main, L.aux.empty() ? nullptr : L.aux.data(), L.ev_base.data(), L.ev_done.data()};
+    if ((e = launch_conv_graphed(h, first, count, launches, cs)) != cudaSuccess) return e;
+    if ((e = cudaEventRecord(L.done, L.main)) != cudaSuccess) return e;
+    return cudaStreamWaitEvent(h->stream, L.done, 0);
+}
+
 }  // namespace
 
 extern "C" {
@@ -332,6 +411,7 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
     if (h->d_seg) cudaFree(h->d_seg);
     conv_drop_graphs(h);
+    destroy_lanes(h);
     for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : h->ev_done) if (ev) cudaEventDestroy(ev);
@@ -387,6 +467,7 @@ int sspyr_upload(sspyr_handle h, int frame, const void* host, size_t pitch_bytes
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaMemcpy2DAsync(h->d_in + (size_t)frame * h->in_frame_bytes, h->in_pitch_bytes, host, pitch_bytes,
                             row, h->cfg.height, cudaMemcpyHostToDevice, h->stream));
+    CU(h, mark_tail(h));
     if (h->ext_in[frame]) conv_drop_graphs(h);
     h->ext_in[frame] = nullptr;
     h->built[frame] = 0;
@@ -404,6 +485,7 @@ int sspyr_set_input_device(sspyr_handle h, int frame, const void* dev, size_t pi
     }
     if (h->ext_in[frame] != dev || h->ext_pitch[frame] != pitch_bytes) conv_drop_graphs(h);   // pointers are baked in
     h->ext_in[frame] = dev;
+    if (dev) h->strict_order = true;     // produced by the caller's own work on the stream: builds follow the whole stream
     h->ext_pitch[frame] = pitch_bytes;
     h->built[frame] = 0;
     return SSPYR_OK;
@@ -433,11 +515,17 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
             int n = 1;
             if (!h->ext_in[f0])
                 while (done + n < count && f0 + n < h->cfg.frames && !h->ext_in[f0 + n]) ++n;
-            e = launch_conv_graphed(h, f0, n, &launches);
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            const int nlanes = lane_count(h);
+            if (nlanes > 1 && cudaStreamIsCapturing(h->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+                e = build_on_lane(h, f0, n, nlanes, &launches);
+            else
+                e = launch_conv_graphed(h, f0, n, &launches, own_streams(h));
             done += n;
         }
         for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
             e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
+        if (e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA)) e = mark_tail(h);
     }
     if (e != cudaSuccess) {
         h->seg_dirty = true;                                 // some levels may have counted this build, others not
@@ -500,6 +588,7 @@ int sspyr_last_launches(sspyr_handle h) { return h ? h->last_launches : SSPYR_ER
 
 int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind, void** ptr) {
     if (!h || !ptr) return SSPYR_ERR_ARG;
+    h->strict_order = true;       // the caller's own kernels may now touch the slots: builds follow the whole stream
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (kind == SSPYR_KIND_EXTREMA) {
         if (!h->d_ext) return fail(h, SSPYR_ERR_STATE, "extrema output not configured");
@@ -520,7 +609,9 @@ int sspyr_download(sspyr_handle h, int frame, int octave, int level, int kind, v
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
     void* src = nullptr;
+    const bool strict = h->strict_order;                     // (the pointer does not leave the library here)
     const int rc = sspyr_device_ptr(h, frame, octave, level, kind, &src);
+    h->strict_order = strict;
     if (rc) return rc;
     const OctGeom& g = h->oct[octave];
     const size_t es = kind == SSPYR_KIND_EXTREMA ? 1 : sizeof(float);
@@ -548,6 +639,7 @@ int sspyr_download_inplace(sspyr_handle h, int frame, float* dst) {
         CU(h, copy_planes_to_host(dst, src, g.W, g.pitch, (size_t)nl * g.H, h->stream));
         dst += (size_t)nl * g.H * g.W;
     }
+    CU(h, mark_tail(h));
     return SSPYR_OK;
 }
 
@@ -566,6 +658,7 @@ int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
         CU(h, copy_planes_to_host(dst, base + (size_t)(2 * nl - 2) * g.plane, g.W, g.pitch, g.H, h->stream));
         dst += (size_t)g.H * g.W;
     }
+    CU(h, mark_tail(h));
     return SSPYR_OK;
 }
 
@@ -800,6 +893,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
     else if (!std::strcmp(key, "conv_l2hint")) h->tune.conv_l2hint = value;
+    else if (!std::strcmp(key, "conv_lanes")) h->tune.conv_lanes = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);
     return SSPYR_OK;
 }

@@ -66,6 +66,8 @@ struct Tuning {
     int conv_fused_sync = 1;   // CONV peer bands: wait/signal inside the strip kernel (0 = one-thread kernels around it)
     int conv_graph = 1;        // CONV: replay the per-frame launch sequence as a CUDA graph from its 2nd use on
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
+    int conv_lanes = 8;        // CONV: builds of different frame slots in flight at once (stream sets, <= 16), 1 = one at a
+                               // time (measured, 1080p: 1 lane 0.163, 4 lanes 0.080 (5 slots) / 0.062, 8 lanes 0.056 ms per frame)
     int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
                                // as the segments of the previous level it reads are published (per-segment counters),
                                // instead of after the whole previous grid (0 = grid-wide dependency only)
@@ -130,6 +132,24 @@ struct sspyr_ctx {
     std::vector<GraphEntry> graphs;          // CONV: captured whole-pyramid launch sequences, by (first slot, count)
     std::vector<cudaStream_t> aux;           // CONV: one extra stream per octave >= 1
     std::vector<cudaEvent_t> ev_base, ev_done;
+    // CONV frame lanes (unbanded handles with several frame slots): a build runs on the stream set of lane
+    // (first slot % lanes) and is joined back into the handle's stream at once, so everything the caller enqueues
+    // afterwards still sees it complete -- but the NEXT build, on another lane, only waits for the library's own
+    // earlier operations on the handle's stream (uploads, downloads, extrema: ev_tail), not for this one.  A pyramid
+    // is a chain of 18+ dependent level kernels; several frames in flight hide that latency (1080p: 3-4x).
+    struct Lane {
+        cudaStream_t main = nullptr;
+        std::vector<cudaStream_t> aux;
+        std::vector<cudaEvent_t> ev_base, ev_done;
+        cudaEvent_t done = nullptr;          // end of the lane's latest build
+        unsigned seen_tail = 0;              // tail_seq the lane has already waited for
+    };
+    std::vector<Lane> lanes;
+    std::vector<int> slot_lane;              // lane of the latest build that wrote a slot (-1: none)
+    cudaEvent_t ev_tail = nullptr;           // latest library operation on the handle's stream that a build must follow
+    unsigned tail_seq = 0;
+    bool strict_order = false;               // raw device pointers were handed out / taken in: every build follows the
+                                             // whole stream (the caller's own kernels may read or write the slots)
     bool timed = false;
     int last_launches = 0;
     int last_first = 0, last_count = 0;      // frame slots the previous kernel wrote (PDL overlap guard)
@@ -141,9 +161,16 @@ namespace sspyr {
 
 // Launchers (defined in the kernel translation units).  Return cudaError_t; *launches += kernels enqueued.
 cudaError_t launch_ref(sspyr_ctx* h, int first_frame, int count, int outputs, int* launches);
-cudaError_t launch_conv(sspyr_ctx* h, int first_frame, int count, int* launches);
+// the stream set a whole-pyramid CONV build runs on: the handle's own, or one of its lanes
+struct ConvStreams {
+    cudaStream_t main;
+    cudaStream_t* aux;           // octaves - 1 streams (or null)
+    cudaEvent_t* ev_base;
+    cudaEvent_t* ev_done;
+};
+cudaError_t launch_conv(sspyr_ctx* h, int first_frame, int count, int* launches, const ConvStreams& cs);
 cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches);
-cudaError_t launch_conv_graphed(sspyr_ctx* h, int first_frame, int count, int* launches);
+cudaError_t launch_conv_graphed(sspyr_ctx* h, int first_frame, int count, int* launches, const ConvStreams& cs);
 void conv_drop_graphs(sspyr_ctx* h);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,
                              int* launches, bool chain = false);

@@ -299,3 +299,37 @@ def test_level_chaining_survives_retuning_and_graph_replay(pkg, O, synth):
             ref = O.conv_build(img, octs, 3)
             check(ss.download_gauss(0), ref["gauss"], 255.0, f"waves {waves}")
             check(ss.download_dog(0), ref["dog"], 255.0, f"waves {waves}")
+
+
+def test_frame_lanes_keep_stream_order(pkg, synth):
+    """CONV builds of different frame slots run on separate stream sets (lanes) and overlap; uploads, downloads,
+    batch calls that span lanes and rebuilds of a slot must still behave as if everything ran in stream order:
+    same bits as the one-build-at-a-time handle (conv_lanes=1) for a mixed sequence of calls."""
+    h, w, octs, n = 300, 520, 4, 6
+
+    def run(lanes):
+        res = []
+        with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n, outputs=pkg.OUT_ALL | pkg.OUT_EXTREMA) as ss:
+            ss.set_tuning(conv_lanes=lanes)
+            for rnd in range(3):
+                for f in range(n):                       # upload -> build per slot, nothing waits in between
+                    ss.upload(synth.noise(h, w, frame=100 * rnd + f), frame=f)
+                    ss.build(f)
+                ss.build_batch(1, 3)                     # slots 1..3 again, as one batch on one lane
+                ss.upload(synth.noise(h, w, frame=100 * rnd + 50), frame=2)
+                ss.build(2)                              # ... and slot 2 once more with new pixels, on its own lane
+                ss.build(5)
+                for f in (0, 2, 3, 5):
+                    res.append(ss.download_gauss(f) + ss.download_dog(f))
+                res.append([ss.download_inplace(1)])
+        return res
+
+    a, b = run(1), run(4)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        for p, q in zip(x, y):
+            if isinstance(p, list):
+                for pp, qq in zip(p, q):
+                    np.testing.assert_array_equal(pp, qq)
+            else:
+                np.testing.assert_array_equal(p, q)
