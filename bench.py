@@ -240,6 +240,8 @@ def run_native(args) -> dict:
         slots = 2
     if args.mode == "conv" and part == "batch":
         slots = 8                                 # CONV launches one kernel per LEVEL for all slots of a batch call
+    if args.mode == "conv" and part == "rowband" and world > 1:
+        slots = 3                                 # CONV row bands keep up to 3 builds in flight (frame lanes, per-slot counters)
     if args.mode == "conv" and part == "replica":
         slots = 8                                 # CONV keeps up to 8 single-frame builds in flight (frame lanes)
     if args.slots > 0:

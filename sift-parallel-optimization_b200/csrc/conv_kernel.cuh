@@ -40,7 +40,7 @@ constexpr int CONV_THREADS = 256;
 
 // input kinds of a level kernel
 constexpr int CONV_FLAG_STRIDE = 32;      // progress-counter values per build (>= levels)
-constexpr int CONV_FLAG_TIMEOUT = 16;     // d_flag[0..15]: per-octave counters; d_flag[16]: wait-timeout marker
+constexpr int CONV_FLAG_TIMEOUT = 16;     // d_flag[0..15]: per-octave counters; d_flag[16]: wait-timeout marker (slot 0's block)
 constexpr int CONV_SRC_PLANE = 3;       // float plane of the previous level (SSPYR_PIXEL_* = 0,1,2 are raw frames)
 
 struct ConvParams {

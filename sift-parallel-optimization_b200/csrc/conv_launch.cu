@@ -220,26 +220,30 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     // The strip kernel does both itself (edge CTAs wait, the last CTA signals); the tile kernel (R > 12) gets
     // one-thread wait / signal kernels around it.
     const bool peered = peered_any;
-    const unsigned epoch = (h->build_seq - 1) * CONV_FLAG_STRIDE;
+    // (a banded build covers one frame slot: `first`; every slot has its own counters, so builds of different
+    //  slots can be in flight at once)
+    unsigned* my_flags = h->d_flag + (size_t)CONV_FLAG_BLOCK * first;
+    const size_t peer_block = (size_t)CONV_FLAG_BLOCK * first;
+    const unsigned epoch = (h->build_seq[first] - 1) * CONV_FLAG_STRIDE;
     const bool first_level = octave == 0 && level == 0;
     const int wo = (level == 1 && octave > 0) ? octave - 1 : octave;
     const unsigned need = epoch + (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;
     const bool fused_sync = peered && march && h->tune.conv_fused_sync != 0;
     if (fused_sync) {
         if (!first_level) {
-            P.wait_up = h->peer[0].attached ? h->peer[0].flag + wo : nullptr;
-            P.wait_dn = h->peer[1].attached ? h->peer[1].flag + wo : nullptr;
+            P.wait_up = h->peer[0].attached ? h->peer[0].flag + peer_block + wo : nullptr;
+            P.wait_dn = h->peer[1].attached ? h->peer[1].flag + peer_block + wo : nullptr;
             P.wait_need = need;
         }
-        P.signal_flag = h->d_flag + octave;
+        P.signal_flag = my_flags + octave;
         P.signal_value = epoch + (unsigned)level + 1;
-        P.done_count = h->d_flag + 32 + octave;
+        P.done_count = my_flags + 32 + octave;
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
         P.src_evict_first = h->tune.conv_l2hint != 0 && level >= 1;
     } else if (peered && !first_level) {
         for (int side = 0; side < 2; ++side)
             if (h->peer[side].attached) {
-                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + wo, 1, need, h->d_flag);
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + peer_block + wo, 1, need, h->d_flag);
                 ++*launches;
             }
     }
@@ -247,7 +251,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {
-        conv_signal_kernel<<<1, 1, 0, st>>>(h->d_flag + octave, epoch + (unsigned)level + 1);
+        conv_signal_kernel<<<1, 1, 0, st>>>(my_flags + octave, epoch + (unsigned)level + 1);
         ++*launches;
         e = cudaGetLastError();
     }
@@ -256,14 +260,14 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
 
 // Start of a build on a band with attached neighbours: next epoch; nothing of this build may be written before
 // both neighbours have finished reading the previous one (every octave counter at its end-of-build value).
-cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches) {
+cudaError_t conv_begin_build(sspyr_ctx* h, int slot, cudaStream_t st, int* launches) {
     if (!(h->peer[0].attached || h->peer[1].attached)) return cudaSuccess;
-    const unsigned b = ++h->build_seq;
+    const unsigned b = ++h->build_seq[slot];
     if (b >= 2) {
         const unsigned prev_done = (b - 2) * CONV_FLAG_STRIDE + (unsigned)h->nl;
         for (int side = 0; side < 2; ++side)
             if (h->peer[side].attached) {
-                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag, h->octaves, prev_done, h->d_flag);
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + (size_t)CONV_FLAG_BLOCK * slot, h->octaves, prev_done, h->d_flag);
                 ++*launches;
             }
     }
@@ -276,7 +280,7 @@ cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches) {
 // back at the end -- the small octaves' short kernels hide behind the large ones instead of queueing after them.
 cudaError_t launch_conv(sspyr_ctx* h, int first, int count, int* launches, const ConvStreams& cs) {
     const int S = h->cfg.S;
-    if (conv_begin_build(h, cs.main, launches) != cudaSuccess) return cudaGetLastError();
+    if (conv_begin_build(h, first, cs.main, launches) != cudaSuccess) return cudaGetLastError();
     const bool fork = h->tune.conv_streams != 0 && h->octaves > 1 && cs.aux != nullptr;
     cudaError_t e;
     if (!fork) {

@@ -181,7 +181,11 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * CONV_TW;
-    const int y_begin = blockIdx.y * seg_rows;
+    // Row bands over peer memory: CTAs are dispatched in blockIdx order, so the two segments at the band edges --
+    // the only ones that wait for a neighbour GPU -- are mapped to the LAST y indices: they start when the interior
+    // is already under way (the neighbour has usually published by then) and never keep interior CTAs off the SMs.
+    const int seg = (P.wait_up || P.wait_dn) ? (int)((blockIdx.y + 1) % gridDim.y) : (int)blockIdx.y;
+    const int y_begin = seg * seg_rows;
     const size_t fz = blockIdx.z;
     // Programmatic dependent launch along the level chain.
     //   * no segment counters (row bands, tile-kernel neighbours): the next level may be scheduled while this one

@@ -119,9 +119,15 @@ cudaError_t mark_tail(sspyr_ctx* h) {
 }
 
 int lane_count(const sspyr_ctx* h) {
-    if (h->cfg.mode != SSPYR_MODE_CONV || h->cfg.full_height != h->cfg.height || h->tune.timing) return 1;
-    if (h->peer[0].attached || h->peer[1].attached) return 1;
+    if (h->cfg.mode != SSPYR_MODE_CONV || h->tune.timing) return 1;
     int n = h->tune.conv_lanes < h->cfg.frames ? h->tune.conv_lanes : h->cfg.frames;
+    if (h->cfg.full_height != h->cfg.height) {
+        // Row bands reading their neighbours' planes in place (every slot has its own progress counters): the CTAs
+        // at a band edge spin until the neighbour GPU has published the level they read, so the builds in flight
+        // are kept few enough that waiting CTAs can never fill a GPU.  Bands driven level by level from the host
+        // (no peers attached) never come here.
+        if (n > 3) n = 3;
+    }
     return n < 1 ? 1 : (n > 16 ? 16 : n);
 }
 
@@ -327,7 +333,7 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
     h->in_pitch_bytes = round_up(in_row, 128);
     h->in_frame_bytes = round_up(h->in_pitch_bytes * cfg.height + 128, 256);
     auto dmalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256); };
-    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * (h->frame_floats * cfg.frames + 64))) != cudaSuccess ||
+    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * (h->frame_floats * cfg.frames + (size_t)CONV_FLAG_BLOCK * cfg.frames))) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_in, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_tables, sizeof(float) * h->h_tables.size())) != cudaSuccess) {
         cudaGetLastError();
@@ -375,7 +381,8 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
         }
     }
     h->d_flag = reinterpret_cast<unsigned*>(h->d_out + h->frame_floats * cfg.frames);   // inside d_out: one IPC handle covers it
-    if ((e = cudaMemset(h->d_flag, 0, 64 * sizeof(float))) != cudaSuccess)
+    h->build_seq.assign(cfg.frames, 0);
+    if ((e = cudaMemset(h->d_flag, 0, (size_t)CONV_FLAG_BLOCK * cfg.frames * sizeof(float))) != cudaSuccess)
         return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
     if ((e = cudaMemcpy(h->d_tables, h->h_tables.data(), sizeof(float) * h->h_tables.size(),
                         cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -759,7 +766,7 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
     CU(h, cudaSetDevice(h->device));
     int launches = 0;
     if (octave == 0 && level == 0) {
-        const cudaError_t e0 = conv_begin_build(h, h->stream, &launches);
+        const cudaError_t e0 = conv_begin_build(h, frame, h->stream, &launches);
         if (e0 != cudaSuccess) return fail_cuda(h, e0, "kernel launch");
     }
     const cudaError_t e = launch_conv_step(h, frame, 1, octave, level, h->stream, &launches);

@@ -14,6 +14,9 @@
 
 namespace sspyr {
 
+constexpr int CONV_FLAG_BLOCK = 64;       // CONV peer counters per frame slot: slot f uses d_flag[64 f ..): [0..15] per-octave
+                                          // progress, [32..47] finished-CTA counts ([16] of slot 0: wait-timeout marker)
+
 // ---- per-octave geometry of one frame slot -------------------------------------------------------
 struct OctGeom {
     int H = 0, W = 0;          // H>>o, W>>o                      (GuassDePyramid.h:66)
@@ -126,7 +129,7 @@ struct sspyr_ctx {
     size_t seg_off[SSPYR_MAX_OCTAVES] = {0};     // first counter of an octave inside a slot
     size_t seg_cap[SSPYR_MAX_OCTAVES] = {0};     // counters per level of that octave (strips x ceil(H/32))
     bool seg_dirty = false;                      // counters may be out of step (tuning changed, failed build): zero them first
-    unsigned build_seq = 0;                      // builds started so far (all bands issue the same sequence)
+    std::vector<unsigned> build_seq;             // per frame slot: builds started so far (all bands issue the same sequence)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     struct GraphEntry { int first, count, seen, launches; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;          // CONV: captured whole-pyramid launch sequences, by (first slot, count)
@@ -169,7 +172,7 @@ struct ConvStreams {
     cudaEvent_t* ev_done;
 };
 cudaError_t launch_conv(sspyr_ctx* h, int first_frame, int count, int* launches, const ConvStreams& cs);
-cudaError_t conv_begin_build(sspyr_ctx* h, cudaStream_t st, int* launches);
+cudaError_t conv_begin_build(sspyr_ctx* h, int slot, cudaStream_t st, int* launches);
 cudaError_t launch_conv_graphed(sspyr_ctx* h, int first_frame, int count, int* launches, const ConvStreams& cs);
 void conv_drop_graphs(sspyr_ctx* h);
 cudaError_t launch_conv_step(const sspyr_ctx* h, int first_frame, int count, int octave, int level, cudaStream_t st,

@@ -333,3 +333,48 @@ def test_frame_lanes_keep_stream_order(pkg, synth):
                     np.testing.assert_array_equal(pp, qq)
             else:
                 np.testing.assert_array_equal(p, q)
+
+
+@pytest.mark.parametrize("world,slots", [(2, 3), (3, 2)])
+def test_peer_bands_with_several_builds_in_flight(pkg, synth, world, slots):
+    """Row bands reading their neighbours' planes in place, whole-pyramid builds (one library call per band and
+    slot, as bench.py runs them on N GPUs), several frame slots in flight on frame lanes: every slot has its own
+    progress counters.  All bands live on one GPU here, each with its own stream; must equal the unbanded build
+    bit for bit, slot by slot, build after build."""
+    import torch
+    h, w, octs, S = 384, 520, 3, 3
+    bands = [pkg.band_rows(h, octs, world, r) for r in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    hs = []
+    for (row0, rows), st in zip(bands, streams):
+        b = pkg.ScaleSpace(rows, w, octs, S, mode=pkg.MODE_CONV, band_row0=row0, full_height=h, frames=slots)
+        b.set_stream(st.cuda_stream)
+        hs.append(b)
+    for i, b in enumerate(hs):
+        if i > 0:
+            b.peer_attach_local(0, hs[i - 1])
+        if i + 1 < world:
+            b.peer_attach_local(1, hs[i + 1])
+    with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV) as whole:
+        for rnd in range(3):
+            imgs = [synth.noise(h, w, frame=10 * rnd + f) for f in range(slots)]
+            for (row0, rows), b in zip(bands, hs):
+                for f in range(slots):
+                    b.upload(np.ascontiguousarray(imgs[f][row0:row0 + rows]), frame=f)
+                b.sync()
+            for f in range(slots):                       # nothing waits between these calls
+                for b in hs:
+                    b.build(f)
+            for b in hs:
+                b.sync()
+            for f in range(slots):
+                whole.upload(imgs[f])
+                whole.build()
+                want = whole.download_gauss() + whole.download_dog()
+                for (row0, rows), b in zip(bands, hs):
+                    got = b.download_gauss(f) + b.download_dog(f)
+                    for o in range(octs):
+                        np.testing.assert_array_equal(got[o], want[o][:, row0 >> o:(row0 >> o) + (rows >> o)])
+                        np.testing.assert_array_equal(got[octs + o], want[octs + o][:, row0 >> o:(row0 >> o) + (rows >> o)])
+    for b in hs:
+        b.close()
