@@ -166,7 +166,8 @@ SSPYR_API int sspyr_download(sspyr_handle h, int frame, int octave, int level, i
 SSPYR_API int sspyr_download_inplace(sspyr_handle h, int frame, float* dst);
 /* Same for all Gaussian levels: S+3 planes per octave. */
 SSPYR_API int sspyr_download_gauss(sspyr_handle h, int frame, float* dst);
-/* Device pointer of a plane (valid until sspyr_destroy). */
+/* Device pointer of a plane (valid until sspyr_destroy).  From the first call on, CONV builds are ordered after
+ * everything already enqueued on the handle's stream (the caller's kernels may now read the planes). */
 SSPYR_API int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind, void** ptr);
 
 /* ---- pinned host memory: lets a C/C++ caller get async copies without including CUDA headers ------- */
@@ -179,7 +180,13 @@ SSPYR_API int sspyr_host_free(void* ptr);
 SSPYR_API int sspyr_window_table(sspyr_handle h, int octave, int level, int axis, float* dst, int capacity);
 /* CONV mode: taps of level s (2R+1 floats, centre at R); returns R through *radius. */
 SSPYR_API int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* radius);
-/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing","conv_tall","conv_streams","conv_pipe","conv_march","conv_graph","conv_tma","conv_waves","conv_seg_min","occ","prefetch_next"}; 0 = default. */
+/* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing","conv_tall","conv_streams",
+ * "conv_pipe","conv_march","conv_graph","conv_tma","conv_waves","conv_seg_min","conv_fused_sync","conv_chain",
+ * "conv_l2hint","conv_lanes","occ","prefetch_next"}.  The two that change behaviour a caller can observe:
+ *   conv_lanes  (default 8) CONV builds of different frame slots that may be in flight at once; 1 = strictly one
+ *               after the other.  Work enqueued on the handle's stream after a build always sees it complete.
+ *   conv_chain  (default 1) consecutive levels of an octave overlap through per-segment counters; 0 = a level
+ *               starts when the previous grid has completed; 2 = chained even for grids of less than a wave. */
 SSPYR_API int sspyr_set_tuning(sspyr_handle h, const char* key, int value);
 
 /* ---- row-band halo exchange (CONV mode, multi-GPU): see DESIGN.md "Row bands" ----------------------- */
