@@ -778,6 +778,7 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
             if (e2 != cudaSuccess) return fail_cuda(h, e2, "kernel launch");
         }
         h->built[frame] = 1;
+        CU(h, mark_tail(h));                                 // a later whole-pyramid build on a frame lane follows this
     }
     return SSPYR_OK;
 }
@@ -880,7 +881,14 @@ int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
 
 int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     if (!h || !key) return SSPYR_ERR_ARG;
+    // Retuning is rare and changes how the next build is issued (other streams, other segment grid, no captured
+    // launch sequences): let everything in flight finish first -- every lane has been joined into the stream --
+    // and make the next lane build follow this point.
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
     conv_drop_graphs(h);
+    mark_tail(h);
+    cudaGetLastError();
     h->seg_dirty = true;                                     // the segment geometry of the next build may differ
     if (!std::strcmp(key, "rows_per_thread")) h->tune.rows_per_thread = value;
     else if (!std::strcmp(key, "block")) h->tune.block = value;
