@@ -239,7 +239,6 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         P.signal_value = epoch + (unsigned)level + 1;
         P.done_count = my_flags + 32 + octave;
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
-        P.src_evict_first = h->tune.conv_l2hint != 0 && level >= 1;
     } else if (peered && !first_level) {
         for (int side = 0; side < 2; ++side)
             if (h->peer[side].attached) {
