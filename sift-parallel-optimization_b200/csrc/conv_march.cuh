@@ -15,9 +15,14 @@
 //
 // so the row pass runs once per input row (only the 2R warm-up rows of a segment are extra), every thread has
 // the same amount of work in every phase, the loads of the next step overlap the column pass of this one
-// without a second staging buffer, and shared memory per CTA drops to ~44 KB (3-5 CTAs per SM).  The DoG
-// centre values come from a 128-bit re-read of the input row (an L2 hit: the row was staged a few steps ago).
-// Segments are sized so that the grid is about one co-resident wave.
+// without a second staging buffer, and shared memory per CTA drops to ~44 KB (4 CTAs per SM).  The DoG centre
+// values are read out of the staged tile before it is handed to the next step's loads (the first R rows of a step,
+// staged one step earlier, are re-read from L2).  Segments are 8 steps long where the level is large enough.
+//
+// Schedule across launches: consecutive levels of an octave are CHAINED -- every (strip, segment)
+// CTA counts its builds in a per-slot counter and the next level's CTAs wait for the 3x3 segments they read instead
+// of for the whole grid; row bands over peer memory wait for / signal the neighbour GPU's per-slot progress
+// counters from their two edge segments, which are dispatched last.
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 
