@@ -343,7 +343,7 @@ def run_native(args) -> dict:
     launch_ms = my_ms / max(my_dominant, 1)
     achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if my_dominant else 0.0
     achieved = dist.sum(achieved) / world                                      # mean per-GPU achieved GB/s
-    traffic = ncu_traffic(args.workload)
+    traffic = ncu_traffic(args.workload if args.mode == "ref" else "conv:" + args.workload)
 
     # ---- end to end through the C ABI with HOST buffers ----------------------------------------------
     e2e = None
