@@ -369,7 +369,7 @@ def run_native(args) -> dict:
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "launch_us": round(launch_ms * 1e3, 3),
-                     "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_level_kernel",
+                     "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_strip_kernel (one launch per level)",
                      "bytes_model": "B_full: input read once + every output plane written once" if args.mode == "ref"
                      else "per-level: input plane read + G_s, DoG_{s-1}, decimated base written, summed over the level launches",
                      "b_full_frac": round(frame_bytes * my_frames * steps / (my_ms * 1e-3) / 1e9 / peak, 4) if my_ms else None},

@@ -30,11 +30,11 @@
 #pragma once
 #include <cuda_pipeline_primitives.h>
 
+#include "conv_sched.h"
 #include "sspyr_internal.h"
 
 namespace sspyr {
 
-constexpr int CONV_TW = 128;            // tile width (outputs)
 constexpr int CONV_PX = 16;             // outputs per thread in the row pass
 constexpr int CONV_THREADS = 256;
 

@@ -189,16 +189,14 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     const bool march = level_marches(h, level);
     const bool peered_any = h->peer[0].attached || h->peer[1].attached;
     const int seg_rows = march_seg_rows(g.H, g.W, count, sms, h->tune.conv_waves, h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32);
-    const long long ctas = (long long)((g.W + CONV_TW - 1) / CONV_TW) * ((g.H + seg_rows - 1) / seg_rows) * count;
+    const long long ctas = march_ctas(g.H, g.W, count, seg_rows);
     // Level chaining (whole-pyramid builds of an unbanded handle): the strip kernels of one octave count finished
     // segments; a level whose source plane was produced by a chained strip kernel of the same octave (same grid)
     // waits per segment instead of per grid.  The first level of a chain -- octave 0 level 0 from the raw frame,
     // or level 1 of a later octave, whose base comes from the octave above through an event -- keeps the grid-wide
-    // dependency.
-    // Only grids of more than one wave are chained: a smaller level has no idle tail to fill, all of its CTAs run
-    // at once and finish together, and the counter handshake then only adds latency (1080p: 5 % slower).
-    if (chain && march && h->d_seg && (h->tune.conv_chain > 1 || (h->tune.conv_chain == 1 && ctas > 4LL * sms)) && !peered_any &&
-        !conv_has_up(h) && !conv_has_down(h)) {
+    // dependency.  Only grids of more than one wave are chained (level_chained, conv_sched.h).
+    if (chain && march && h->d_seg && level_chained(h->tune.conv_chain, ctas, sms) && !peered_any && !conv_has_up(h) &&
+        !conv_has_down(h)) {
         unsigned* lv0 = h->d_seg + (size_t)first * h->seg_frame_stride + h->seg_off[octave];
         P.seg_pub = lv0 + (size_t)level * h->seg_cap[octave];
         P.seg_frame_stride = (unsigned)h->seg_frame_stride;

@@ -30,8 +30,6 @@
 
 namespace sspyr {
 
-constexpr int STRIP_TH = 32;             // output rows per step
-
 // ---- TMA (cp.async.bulk.tensor) + mbarrier helpers --------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -462,33 +460,11 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     }
 }
 
-// Vertical segmentation of a level for the strip kernel: about `waves` co-resident waves of CTAs (4 per SM for every
-// radius <= 12), segments of a multiple of 32 rows, at least seg_min.  Depends on the plane geometry only, so all
-// levels of an octave get the same (strip, segment) grid -- which the level chaining relies on.
-// waves <= 0: automatic -- 3 waves, but segments of at least `long_rows` rows (8 steps: the 2R warm-up rows and the
-// exposed first load are paid once per segment) as long as that still leaves 1.5 waves; measured on 8K: 5-step
-// segments x 2.7 waves 0.683 ms, 8-step x 1.7 waves 0.668 ms, 4-step x 3.4 waves 0.734 ms per pyramid.
-inline int march_seg_rows(int H, int W, int frames, int sms, int waves, int seg_min, int long_rows = 8 * STRIP_TH) {
-    const long long strips = (long long)((W + CONV_TW - 1) / CONV_TW) * frames;
-    auto rows_for = [&](long long ctas) {
-        long long segs = ctas / strips;
-        if (segs < 1) segs = 1;
-        const int r = (int)((H + segs - 1) / segs);
-        return (r + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
-    };
-    int seg_rows = rows_for((long long)sms * 4 * (waves > 0 ? waves : 3));
-    if (waves <= 0 && seg_rows < long_rows) {
-        const long long ctas_long = strips * ((H + long_rows - 1) / long_rows);
-        if (2 * ctas_long >= 3LL * sms * 4) seg_rows = long_rows;
-    }
-    return seg_rows < seg_min ? seg_min : seg_rows;
-}
-
 template <int R, int SRC, bool TMA>
 cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, const CUtensorMap& tmap,
                              int seg_rows, bool pdl) {
     constexpr size_t smem = strip_smem_bytes<R>();
-    static_assert(smem + 1024 <= (227 * 1024) / 4, "4 CTAs per SM");
+    static_assert(smem + 1024 <= (227 * 1024) / STRIP_CTAS_PER_SM, "the segmentation counts on 4 CTAs per SM");
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <new>
 
+#include "conv_sched.h"
 #include "sspyr_internal.h"
 
 using namespace sspyr;
@@ -120,15 +121,8 @@ cudaError_t mark_tail(sspyr_ctx* h) {
 
 int lane_count(const sspyr_ctx* h) {
     if (h->cfg.mode != SSPYR_MODE_CONV || h->tune.timing) return 1;
-    int n = h->tune.conv_lanes < h->cfg.frames ? h->tune.conv_lanes : h->cfg.frames;
-    if (h->cfg.full_height != h->cfg.height) {
-        // Row bands reading their neighbours' planes in place (every slot has its own progress counters): the CTAs
-        // at a band edge spin until the neighbour GPU has published the level they read, so the builds in flight
-        // are kept few enough that waiting CTAs can never fill a GPU.  Bands driven level by level from the host
-        // (no peers attached) never come here.
-        if (n > 3) n = 3;
-    }
-    return n < 1 ? 1 : (n > 16 ? 16 : n);
+    // (bands driven level by level from the host -- no peers attached -- never come here)
+    return frame_lanes(h->tune.conv_lanes, h->cfg.frames, h->cfg.full_height != h->cfg.height);
 }
 
 cudaError_t ensure_lanes(sspyr_ctx* h, int n) {

@@ -148,3 +148,60 @@ int main() {
     import torch
     rc = subprocess.run([str(tmp_path / "probe")]).returncode
     assert rc == (0 if torch.cuda.is_available() else 42)
+
+
+def test_conv_scheduling_arithmetic(tmp_path):
+    """csrc/conv_sched.h (host-only C++): how CONV levels are cut into (strip, segment) CTAs, which levels are
+    chained, how many builds are in flight.  Compiled with plain g++ and checked on BASELINE.json's shapes and on
+    random geometries: segments are whole 32-row steps that cover the level, identical for every level of an
+    octave (the chaining counters are indexed by them), long where the level is large, and a level of less than a
+    wave is never chained automatically."""
+    src = tmp_path / "sched.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <cstdlib>
+#include "conv_sched.h"
+using namespace sspyr;
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED line %d: %s\n", __LINE__, #c); return 1; } } while (0)
+int main() {
+    const int sms = 148;
+    // BASELINE shapes, octave 0, automatic segmentation (waves = 0), minimum 32 rows
+    CHECK(march_seg_rows(4320, 7680, 1, sms, 0, 32) == 256);            // 8K: 8-step segments, 60 x 17 CTAs = 1.7 waves
+    CHECK(march_ctas(4320, 7680, 1, 256) == 1020);
+    CHECK(march_seg_rows(16384, 16384, 1, sms, 0, 32) == 1280);         // 16K: 3 waves already give 40-step segments
+    CHECK(march_seg_rows(2160, 3840, 8, sms, 0, 32) == 320);            // 4K x 8 frames per launch
+    CHECK(march_seg_rows(1080, 1920, 1, sms, 0, 32) == 32);             // 1080p: one step per CTA (less than a wave)
+    CHECK(march_seg_rows(4320, 7680, 1, sms, 3, 32) == 160);            // explicit wave counts are honoured
+    CHECK(march_seg_rows(4320, 7680, 1, sms, 3, 512) == 512);
+    // chaining: only multi-wave grids unless forced
+    CHECK(level_chained(1, march_ctas(4320, 7680, 1, 256), sms));
+    CHECK(level_chained(1, march_ctas(2160, 3840, 1, march_seg_rows(2160, 3840, 1, sms, 0, 32)), sms));   // 8K octave 1
+    CHECK(!level_chained(1, march_ctas(1080, 1920, 1, 32), sms));
+    CHECK(!level_chained(0, 1 << 20, sms) && level_chained(2, 1, sms));
+    // lanes
+    CHECK(frame_lanes(8, 8, false) == 8 && frame_lanes(8, 5, false) == 5 && frame_lanes(8, 1, false) == 1);
+    CHECK(frame_lanes(8, 8, true) == 3 && frame_lanes(2, 8, true) == 2 && frame_lanes(0, 8, false) == 1);
+    CHECK(frame_lanes(64, 64, false) == 16);
+    // random geometries
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&](int lo, int hi) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return lo + (int)(x % (unsigned long long)(hi - lo + 1)); };
+    for (int it = 0; it < 20000; ++it) {
+        const int H = rnd(1, 20000), W = rnd(1, 20000), frames = rnd(1, 9), waves = rnd(0, 6), seg_min = 32 * rnd(1, 4);
+        const int r = march_seg_rows(H, W, frames, sms, waves, seg_min);
+        CHECK(r % STRIP_TH == 0 && r >= seg_min);
+        const long long ctas = march_ctas(H, W, frames, r);
+        CHECK(ctas >= 1 && (long long)((H + r - 1) / r) * r >= H);
+        if (waves == 0 && r == 8 * STRIP_TH && r > seg_min)              // long segments were chosen: still >= 1.5 waves
+            CHECK(2 * ctas >= 3LL * sms * STRIP_CTAS_PER_SM || march_seg_rows(H, W, frames, sms, 3, seg_min) >= r);
+        if (waves > 0 && r > seg_min)                                    // never more CTAs than the waves asked for (rounding up rows)
+            CHECK(ctas <= (long long)sms * STRIP_CTAS_PER_SM * waves || (H + r - 1) / r == 1);
+    }
+    std::printf("ok\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "sched"
+    subprocess.run(["/usr/bin/g++", "-std=gnu++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "sift-parallel-optimization_b200", "csrc"),
+                    str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout
