@@ -175,3 +175,45 @@ def test_extrema_oracle_finds_a_planted_peak(O):
     dog[1, 2, 6] = -2.0
     f = O.extrema_octave(dog, 0.5)
     assert f.shape == (3, 9, 9) and f.sum() == 2 and f[1, 4, 4] == 1 and f[0, 2, 6] == 1
+
+
+@pytest.mark.parametrize("h,w,octs,S,sigma0,rs", [(96, 130, 3, 3, 1.6, 3.0), (61, 47, 2, 2, 1.2, 4.0), (128, 128, 4, 3, 2.0, 3.0)])
+def test_conv_oracle_against_an_independent_scipy_restatement(O, h, w, octs, S, sigma0, rs):
+    """CONV mode has no upstream parity, so its C oracle (orc_conv_build) is at least checked against a second,
+    independent statement of the same specification (DESIGN.md 'CONV mode') written here with scipy.ndimage:
+    sigma_s = sigma0 * 2^(s/S); G_0 = I * g(sqrt(max(sigma0^2 - sigma_in^2, 0.01))); G_s = G_{s-1} * g(sqrt(sigma_s^2 -
+    sigma_{s-1}^2)); taps exp(-k^2 / 2 sigma^2) over |k| <= ceil(rs * sigma), normalised; clamp-to-edge border; row
+    pass then column pass; next octave = G_S at even rows / columns; DoG_s = G_s - G_{s+1}."""
+    ndi = pytest.importorskip("scipy.ndimage")
+    sigma_in = 0.5
+    sigma0, rs = float(np.float32(sigma0)), float(np.float32(rs))     # the API takes them as C floats
+    rng = np.random.default_rng(5)
+    img = rng.integers(0, 256, (h, w)).astype(np.int32)
+
+    def taps(si):
+        R = max(1, int(np.ceil(rs * si)))
+        k = np.arange(-R, R + 1, dtype=np.float64)
+        t = np.exp(-k * k / (2.0 * si * si))
+        return (t / t.sum()).astype(np.float32).astype(np.float64)
+
+    def blur(a, si):
+        t = taps(si)
+        rows = ndi.correlate1d(a.astype(np.float64), t, axis=1, mode="nearest").astype(np.float32)   # row pass, stored as fp32
+        return ndi.correlate1d(rows.astype(np.float64), t, axis=0, mode="nearest").astype(np.float32)
+
+    sig = [sigma0 * 2.0 ** (s / S) for s in range(S + 3)]
+    inc = [np.sqrt(max(sigma0 ** 2 - sigma_in ** 2, 0.01))] + [np.sqrt(sig[s] ** 2 - sig[s - 1] ** 2) for s in range(1, S + 3)]
+    got = O.conv_build(img, octs, S, sigma0=sigma0, sigma_in=sigma_in, radius_sigmas=rs)
+    base = None
+    for o in range(octs):
+        levels = [blur(img.astype(np.float32), inc[0]) if o == 0 else base]
+        for s in range(1, S + 3):
+            levels.append(blur(levels[-1], inc[s]))
+            mine = O.conv_taps(s, S, sigma0, sigma_in, rs)                    # same radius, taps equal to an fp32 ulp
+            assert mine.size == taps(inc[s]).size
+            np.testing.assert_allclose(mine.astype(np.float64), taps(inc[s]), rtol=2e-7, atol=1e-10)
+        want = np.stack(levels)
+        assert got["gauss"][o].shape == want.shape == (S + 3, h >> o, w >> o)
+        np.testing.assert_allclose(got["gauss"][o], want, rtol=0, atol=2e-5 * 255)
+        np.testing.assert_allclose(got["dog"][o], want[:-1] - want[1:], rtol=0, atol=4e-5 * 255)
+        base = got["gauss"][o][S][::2, ::2][:h >> (o + 1), :w >> (o + 1)]      # (the oracle's own G_S: errors do not compound)
