@@ -31,3 +31,13 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_supplementary_conv_line_never_breaks_the_main_line():
+    """A default single-GPU run appends a CONV-mode figure measured by a child process; whatever happens to the
+    child (here: no GPU at all) the parent gets a small dict back, never an exception or a hang."""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    got = bench.conv_extra(argparse.Namespace(workload="c2"))
+    assert isinstance(got, dict) and ("unavailable" in got or "value" in got)
