@@ -370,6 +370,7 @@ def run_native(args) -> dict:
         "gpu_launches": int(dist.sum(my_launches)),
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "frac_of_nominal_8000": round(achieved / 8000.0, 4),     # north_star's "~8 TB/s" figure, for reference
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "launch_us": round(launch_ms * 1e3, 3),
                      "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_strip_kernel (one launch per level)",
                      "bytes_model": "B_full: input read once + every output plane written once" if args.mode == "ref"
