@@ -26,6 +26,10 @@
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 
+#ifndef SSPYR_STRIP_COLPASS
+#define SSPYR_STRIP_COLPASS 1            // column-pass mapping of the strip kernel: 1 = 4 columns x 4 rows per thread (default)
+#endif
+
 #include "conv_kernel.cuh"
 
 namespace sspyr {
@@ -173,7 +177,13 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     constexpr int TH = STRIP_TH;
     constexpr int PIN = conv_pitch_in<R>();
     constexpr int PT = conv_pitch_t();
-    constexpr int PY = TH / 8;
+    // Column-pass mapping: a thread owns PX adjacent columns x PY rows.  4 x 4 is the measured default; 2 x 8
+    // (SSPYR_STRIP_COLPASS=2, an evaluation build: make EXTRA=-DSSPYR_STRIP_COLPASS=2) reads 8+2R 64-bit words
+    // instead of 4+2R 128-bit ones per 16 outputs: 36 % fewer column-pass shared-memory wavefronts, same FMA count.
+    constexpr int PX = SSPYR_STRIP_COLPASS == 2 ? 2 : 4;
+    constexpr int PY = 16 / PX;
+    constexpr int TPB = CONV_TW / PX;                    // threads per row block of the column pass (32 or 64)
+    static_assert(TPB * (TH / PY) == CONV_THREADS, "column-pass mapping must cover the step");
     constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
     extern __shared__ __align__(128) float smem[];
     float* sIn = smem;                                  // [TH][PIN]     staged input rows (centre at column RA)
@@ -304,8 +314,8 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     __syncthreads();
     strip_row_pass<R, 2 * R, 0>(P, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
 
-    const int cq = tid & 31, rb = tid >> 5;             // column quad / row block of the column pass
-    const int x = x0 + cq * 4;
+    const int cq = tid % TPB, rb = tid / TPB;           // column group / row block of the column pass
+    const int x = x0 + cq * PX;
     const int nvalid = P.W - x;
     float* g = P.dst_g + fz * P.dst_frame_stride;
     float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
@@ -331,25 +341,37 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         // warps that own the first R output rows re-read those rows from global (they were staged one step ago).
         const int y0 = y_begin + k * TH;
         const int yr = y0 + rb * PY;                     // first output row of this thread
-        float cen[PY][4];
-        if (d && nvalid >= 4) {
+        float cen[PY][PX];
+        if (d && nvalid >= PX) {
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
                 const int m = rb * PY + j - R;           // staged row of this step (warp-uniform)
                 if (m >= 0) {
-                    const float4 t = *reinterpret_cast<const float4*>(sIn + (size_t)m * PIN + RA_ + cq * 4);
-                    cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                    const float* c = sIn + (size_t)m * PIN + RA_ + cq * PX;
+                    if constexpr (PX == 4) {
+                        const float4 t = *reinterpret_cast<const float4*>(c);
+                        cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                    } else {
+                        const float2 t = *reinterpret_cast<const float2*>(c);
+                        cen[j][0] = t.x; cen[j][1] = t.y;
+                    }
                 } else {
                     const unsigned char* crow = src + (size_t)min(yr + j, P.H - 1) * P.src_pitch * elem;
-                    if constexpr (SRC == SSPYR_PIXEL_I32) {
-                        const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(crow) + x));
-                        cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
-                    } else if constexpr (SRC == SSPYR_PIXEL_U8) {
-                        const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
-                        cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                    if constexpr (PX == 4) {
+                        if constexpr (SRC == SSPYR_PIXEL_I32) {
+                            const int4 t = __ldg(reinterpret_cast<const int4*>(reinterpret_cast<const int*>(crow) + x));
+                            cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                        } else if constexpr (SRC == SSPYR_PIXEL_U8) {
+                            const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
+                            cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                        } else {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
+                            cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+                        }
                     } else {
-                        const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
-                        cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
+#pragma unroll
+                        for (int i = 0; i < PX; ++i)
+                            cen[j][i] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(crow, (size_t)(x + i));
                     }
                 }
             }
@@ -358,42 +380,65 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         if (k + 1 < nsteps) stage_step(y_begin + R + (k + 1) * TH);   // in flight during the column pass below
 
         // ---- column pass: output rows y0 + rb*PY + j from sT rows rb*PY + j .. + 2R -------------------------
-        const float* tcol = sT + (size_t)(rb * PY) * PT + cq * 4;
-        f32x2 a01[PY], a23[PY];                          // packed accumulators: columns (0,1) and (2,3) of each row
+        const float* tcol = sT + (size_t)(rb * PY) * PT + cq * PX;
+        f32x2 a01[PY], a23[PX == 4 ? PY : 1];            // packed accumulators: columns (0,1) [and (2,3)] of each row
 #pragma unroll
-        for (int j = 0; j < PY; ++j) a01[j] = a23[j] = pk2(0.0f, 0.0f);
+        for (int j = 0; j < PY; ++j) a01[j] = pk2(0.0f, 0.0f);
+        if constexpr (PX == 4) {
+#pragma unroll
+            for (int j = 0; j < PY; ++j) a23[j] = pk2(0.0f, 0.0f);
+        }
 #pragma unroll
         for (int i = 0; i < PY + 2 * R; ++i) {
-            const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
-            const f32x2 v01 = pk2(v.x, v.y), v23 = pk2(v.z, v.w);
+            f32x2 v01, v23 = 0;
+            if constexpr (PX == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(tcol + (size_t)i * PT);
+                v01 = pk2(v.x, v.y);
+                v23 = pk2(v.z, v.w);
+            } else {
+                const float2 v = *reinterpret_cast<const float2*>(tcol + (size_t)i * PT);
+                v01 = pk2(v.x, v.y);
+            }
 #pragma unroll
             for (int j = 0; j < PY; ++j) {
                 if (i - j >= 0 && i - j <= 2 * R) {            // compile-time after unrolling
                     const f32x2 w = pk2(P.taps[i - j], P.taps[i - j]);
                     a01[j] = fma2(w, v01, a01[j]);
-                    a23[j] = fma2(w, v23, a23[j]);
+                    if constexpr (PX == 4) a23[j] = fma2(w, v23, a23[j]);
                 }
             }
         }
-        float acc[PY][4];
+        float acc[PY][PX];
 #pragma unroll
-        for (int j = 0; j < PY; ++j) { unpk2(a01[j], acc[j][0], acc[j][1]); unpk2(a23[j], acc[j][2], acc[j][3]); }
-        if (nvalid >= 4) {                               // full quad: vector stores, one running offset
+        for (int j = 0; j < PY; ++j) {
+            unpk2(a01[j], acc[j][0], acc[j][1]);
+            if constexpr (PX == 4) unpk2(a23[j], acc[j][2], acc[j][3]);
+        }
+        if (nvalid >= PX) {                              // full group: vector stores, one running offset
             unsigned o = (unsigned)yr * (unsigned)P.dst_pitch + (unsigned)x;   // a plane has < 2^32 floats
 #pragma unroll
             for (int j = 0; j < PY; ++j, o += (unsigned)P.dst_pitch) {
                 const int y = yr + j;
                 if (y >= y_end) break;
-                *reinterpret_cast<float4*>(g + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                if (d)                                   // DoG_{s-1} = G_{s-1} - G_s  (GuassDePyramid.h:143)
-                    __stcs(reinterpret_cast<float4*>(d + o), make_float4(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1],
-                                                                         cen[j][2] - acc[j][2], cen[j][3] - acc[j][3]));
+                if constexpr (PX == 4) {
+                    *reinterpret_cast<float4*>(g + o) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    if (d)                               // DoG_{s-1} = G_{s-1} - G_s  (GuassDePyramid.h:143)
+                        __stcs(reinterpret_cast<float4*>(d + o), make_float4(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1],
+                                                                             cen[j][2] - acc[j][2], cen[j][3] - acc[j][3]));
+                } else {
+                    *reinterpret_cast<float2*>(g + o) = make_float2(acc[j][0], acc[j][1]);
+                    if (d) __stcs(reinterpret_cast<float2*>(d + o), make_float2(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1]));
+                }
                 if (dec && (y & 1) == 0) {               // even-phase decimation (GuassDePyramid.h:80)
                     const int dy = y >> 1, dx = x >> 1;
                     if (dy < P.dec_H && dx < P.dec_W) {
                         float* q = dec + (size_t)dy * P.dec_pitch + dx;
-                        if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
-                        else q[0] = acc[j][0];
+                        if constexpr (PX == 4) {
+                            if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
+                            else q[0] = acc[j][0];
+                        } else {
+                            q[0] = acc[j][0];
+                        }
                     }
                 }
             }
@@ -405,7 +450,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                 const size_t o = (size_t)y * P.dst_pitch + x;
                 const unsigned char* crow = src + (size_t)y * P.src_pitch * elem;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < PX; ++i)
                     if (i < nvalid) {
                         g[o + i] = acc[j][i];
                         if (d) __stcs(d + o + i, load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(crow, (size_t)(x + i)) - acc[j][i]);
@@ -415,21 +460,23 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                     if (dy < P.dec_H && dx < P.dec_W) {
                         float* q = dec + (size_t)dy * P.dec_pitch + dx;
                         q[0] = acc[j][0];
-                        if (dx + 1 < P.dec_W && nvalid > 2) q[1] = acc[j][2];
+                        if constexpr (PX == 4) {
+                            if (dx + 1 < P.dec_W && nvalid > 2) q[1] = acc[j][2];
+                        }
                     }
                 }
             }
         }
         // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH).
-        // Only the first CW warps' column passes read the destination rows (rb*PY < 2R), so only they meet at a
-        // named barrier and do the copy; the other warps go straight on to wait for the next step's rows.  The
+        // Only the first CW row blocks' column passes read the destination rows (rb*PY < 2R), so only their warps meet
+        // at a named barrier and do the copy; the other warps go straight on to wait for the next step's rows.  The
         // source rows are not written before the next row pass, which every warp enters through the full barrier
         // at the top of the loop.
-        constexpr int CW = (2 * R + PY - 1) / PY;
-        static_assert(CW * 32 <= CONV_THREADS, "carry warps");
+        constexpr int CW = (2 * R + PY - 1) / PY;        // row blocks whose column pass reads rows [0, 2R)
+        static_assert(CW * TPB <= CONV_THREADS && (CW * TPB) % 32 == 0, "carry warps");
         if (k + 1 < nsteps && rb < CW) {
-            asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
-            for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CW * 32) {
+            asm volatile("bar.sync 1, %0;" ::"n"(CW * TPB) : "memory");
+            for (int c = tid; c < 2 * R * (CONV_TW / 4); c += CW * TPB) {
                 const int rr = c / (CONV_TW / 4), q = c - rr * (CONV_TW / 4);
                 *reinterpret_cast<float4*>(sT + (size_t)rr * PT + 4 * q) = *reinterpret_cast<const float4*>(sT + (size_t)(TH + rr) * PT + 4 * q);
             }
