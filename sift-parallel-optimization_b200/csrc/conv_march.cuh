@@ -29,6 +29,9 @@
 #ifndef SSPYR_STRIP_COLPASS
 #define SSPYR_STRIP_COLPASS 1            // column-pass mapping of the strip kernel: 1 = 4 columns x 4 rows per thread (default)
 #endif
+#ifndef SSPYR_STRIP_EPILOGUE
+#define SSPYR_STRIP_EPILOGUE 1           // 2 = evaluation build: running output pointers + an unchecked interior path
+#endif
 
 #include "conv_kernel.cuh"
 
@@ -321,6 +324,11 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
     float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
 
+    // (evaluation build SSPYR_STRIP_EPILOGUE=2) running pointers to this thread's first output row of the step: the
+    // shipped epilogue rebuilds its 64-bit addresses from block / thread indices every step (~17 instructions) and
+    // every row (~6); these advance by one add per step and per row.
+    [[maybe_unused]] float* gq = g + (size_t)(y_begin + rb * PY) * P.dst_pitch + x;
+    [[maybe_unused]] float* dq = d ? d + (size_t)(y_begin + rb * PY) * P.dst_pitch + x : nullptr;
 #pragma unroll 1
     for (int k = 0; k < nsteps; ++k) {
         if (k > 0) {                                     // (step 0 was awaited in the prologue)
@@ -414,7 +422,35 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             unpk2(a01[j], acc[j][0], acc[j][1]);
             if constexpr (PX == 4) unpk2(a23[j], acc[j][2], acc[j][3]);
         }
-        if (nvalid >= PX) {                              // full group: vector stores, one running offset
+        if (SSPYR_STRIP_EPILOGUE == 2 && nvalid >= PX && yr + PY <= y_end) {      // interior: no per-row checks
+            float* gp = gq;
+            float* dp = dq;
+#pragma unroll
+            for (int j = 0; j < PY; ++j) {
+                if constexpr (PX == 4) {
+                    *reinterpret_cast<float4*>(gp) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+                    if (d) __stcs(reinterpret_cast<float4*>(dp), make_float4(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1],
+                                                                            cen[j][2] - acc[j][2], cen[j][3] - acc[j][3]));
+                } else {
+                    *reinterpret_cast<float2*>(gp) = make_float2(acc[j][0], acc[j][1]);
+                    if (d) __stcs(reinterpret_cast<float2*>(dp), make_float2(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1]));
+                }
+                gp += P.dst_pitch;
+                if (d) dp += P.dst_pitch;
+                if (dec && (j & 1) == 0) {               // yr is even (segments and row blocks are): even j = even row
+                    const int dy = (yr + j) >> 1, dx = x >> 1;
+                    if (dy < P.dec_H && dx < P.dec_W) {
+                        float* q = dec + (size_t)dy * P.dec_pitch + dx;
+                        if constexpr (PX == 4) {
+                            if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
+                            else q[0] = acc[j][0];
+                        } else {
+                            q[0] = acc[j][0];
+                        }
+                    }
+                }
+            }
+        } else if (nvalid >= PX) {                       // full group: vector stores, one running offset
             unsigned o = (unsigned)yr * (unsigned)P.dst_pitch + (unsigned)x;   // a plane has < 2^32 floats
 #pragma unroll
             for (int j = 0; j < PY; ++j, o += (unsigned)P.dst_pitch) {
@@ -466,6 +502,10 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                     }
                 }
             }
+        }
+        if (SSPYR_STRIP_EPILOGUE == 2) {
+            gq += (size_t)TH * P.dst_pitch;
+            if (d) dq += (size_t)TH * P.dst_pitch;
         }
         // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH).
         // Only the first CW row blocks' column passes read the destination rows (rb*PY < 2R), so only their warps meet
