@@ -188,9 +188,9 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     constexpr int TPB = CONV_TW / PX;                    // threads per row block of the column pass (32 or 64)
     static_assert(TPB * (TH / PY) == CONV_THREADS, "column-pass mapping must cover the step");
     constexpr int elem = SRC == SSPYR_PIXEL_U8 ? 1 : 4;
-    extern __shared__ __align__(128) float smem[];
-    float* sIn = smem;                                  // [TH][PIN]     staged input rows (centre at column RA)
-    float* sT = smem + (size_t)TH * PIN;                // [TH+2R][PT]   row-pass results: 2R carried rows + TH new ones
+    extern __shared__ __align__(128) float strip_smem[];   // (own name: the tile kernel's array is declared 16-byte aligned)
+    float* sIn = strip_smem;                            // [TH][PIN]     staged input rows (centre at column RA)
+    float* sT = strip_smem + (size_t)TH * PIN;          // [TH+2R][PT]   row-pass results: 2R carried rows + TH new ones
     // mbarrier of the TMA staging: kept in the dynamic allocation so that sIn stays at its 128-byte aligned base
     unsigned long long& bar = *reinterpret_cast<unsigned long long*>(sT + (size_t)(TH + 2 * R) * PT);
     constexpr int RA_ = conv_ra<R>();
