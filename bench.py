@@ -7,15 +7,21 @@
 One "step" = one pass of the hot path (fused init/decimate + window + DoG, GuassDePyramid.h:60-149) over
 one batch of synthetic frames.  Workloads are BASELINE.json's configs:
 
-  c1  512x512, 4 octaves, 1 frame/step                      (the reference's own CPU-runnable case)
-  c2  1920x1080 single frame, 5 octaves x 6 levels          (DEFAULT: the config the metric is quoted on)
-  c3  3840x2160 x 256 frames, 5 octaves, frames sharded over the ranks (BATCH partition, strong scaling)
+  c1  512x512, 4 octaves, 32 frames per batched launch       (the reference's own CPU-runnable case)
+  c2  1920x1080 single frame, 5 octaves x 6 levels          (r01's default; now the extra record "c2")
+  c3  3840x2160 x 256 frames, 5 octaves, frames sharded over the ranks (BATCH partition, strong scaling; DEFAULT:
+      the config BASELINE.json quotes at "1/2/4/8 B200" -- it fits one GPU through the frame-slot ring)
   c4  7680x4320 single image, 5 octaves, row bands over the ranks      (ROWBAND partition, strong scaling)
   c5  16384x16384, 8 octaves, row bands over the ranks                 (ROWBAND partition, strong scaling)
 
 c1/c2 under N>1 ranks: every rank builds its own frame per step (weak scaling).  No data-path collective
 exists in REF mode (pointwise math: halo radius 0) -- torch.distributed is used for the barrier and the
 max-over-ranks of the timings only.
+
+A default run also appends `extras`: bounded measurements of the other sharded workloads in the same process
+group -- c4 REF row bands, c4 / c5 CONV row bands with halos read over NVLink peer memory inside the blur kernel, c3
+CONV batch, c2 -- each with its own value, ms_per_step, roofline and, under N > 1 ranks, the same workload timed on
+rank 0 alone (`n1`) so that the per-N speed-up is inside the one driver-written file.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events on the launch stream);
 `e2e` = the same metric through the C ABI with pinned HOST buffers (H2D + build + D2H of the reference's
@@ -38,7 +44,7 @@ import __graft_entry__ as entry  # noqa: E402
 
 WORKLOADS = {
     #      H      W     oct frames partition  description
-    "c1": (512, 512, 4, 1, "replica", "512x512 grayscale, 4 octaves x 6 levels (S=3)"),
+    "c1": (512, 512, 4, 32, "replica", "512x512 grayscale, 4 octaves x 6 levels (S=3), 32 frames per batched launch"),
     "c2": (1080, 1920, 5, 1, "replica", "1920x1080 single frame, 5 octaves x 6 levels (S=3)"),
     "c3": (2160, 3840, 5, 256, "batch", "3840x2160 batch of 256 frames, 5 octaves x 6 levels, frames sharded per GPU"),
     "c4": (4320, 7680, 5, 1, "rowband", "7680x4320 single image, 5 octaves x 6 levels, row bands per GPU"),
@@ -54,14 +60,15 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--mode", default="ref", choices=["ref", "conv"])
     ap.add_argument("--outputs", default="all", choices=["all", "inplace"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-conv-extra", action="store_true",
-                    help="skip the supplementary CONV-mode line that a default single-GPU REF run appends as 'conv_mode'")
+    ap.add_argument("--no-extras", "--no-conv-extra", dest="no_extras", action="store_true",
+                    help="skip the extra records (other sharded workloads, CONV mode) a default run appends as 'extras'")
+    ap.add_argument("--extras", default="", help="comma list of extra records to run instead of the default set")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
                     help="CONV row bands: read neighbour planes in the kernel over NVLink (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--slots", type=int, default=0, help="frame slots in the ring (0 = enough to cover 4x L2, 2..8)")
@@ -208,27 +215,34 @@ def rank_geometry(pkg, wl: str, world: int, rank: int):
     return H, 0, H, W, octs, frames
 
 
-def run_native(args) -> dict:
-    import numpy as np
-    import torch
+DEFAULT_STEPS = {"c1": (300, 20), "c2": (2000, 50), "c3": (3, 3), "c4": (200, 10), "c5": (30, 3)}
+_noise_cache: dict = {}
 
-    rank, world, local = dist_env()
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with torch.distributed.run --nproc-per-node N (one rank per GPU)")
-    torch.cuda.set_device(local)
-    dist = Dist(world, local)
-    pkg = entry.load_package()
-    H, W, octs, total_frames, part, desc = WORKLOADS[args.workload]
-    rows, row0, full_h, width, octs, my_frames = rank_geometry(pkg, args.workload, world, rank)
-    mode = pkg.MODE_REF if args.mode == "ref" else pkg.MODE_CONV
-    outputs = pkg.OUT_ALL if args.outputs == "all" else pkg.OUT_INPLACE
-    steps = args.steps if args.steps is not None else {"c1": 2000, "c2": 2000, "c3": 3, "c4": 200, "c5": 30}[args.workload]
-    warmup = args.warmup if args.warmup is not None else {"c1": 50, "c2": 50, "c3": 1, "c4": 10, "c5": 3}[args.workload]
-    warmup = max(warmup, 3)
 
-    sampler = ClockSampler(local)
-    sampler.start()
+def synth_frame(pkg, rows, width, frame, row0):
+    """Synthetic noise frame; gigapixel bands are generated once and reused for every slot (values do not
+    change what the GPU does, and splitmix64 over 268 M pixels costs seconds of numpy per slot)."""
+    if rows * width >= (1 << 26):
+        key = (rows, width, row0)
+        if key not in _noise_cache:
+            _noise_cache.clear()
+            _noise_cache[key] = pkg.synth.noise(rows, width, frame=0, row0=row0)
+        return _noise_cache[key]
+    return pkg.synth.noise(rows, width, frame=frame, row0=row0)
+
+
+def measure(pkg, torch, dist, sampler, wl: str, mode_name: str, outputs_name: str, world: int, rank: int, local: int,
+            steps: int | None, warmup: int | None, halo: str = "peer", tune: str = "", slots_arg: int = 0,
+            per_step_pass: bool = True) -> dict:
+    """Device-resident throughput of one workload on the ranks of `dist` (world may be 1 inside a larger job: the
+    caller then runs this on rank 0 only).  Returns the JSON fields of one record (no e2e, no CPU baseline)."""
+    H, W, octs, total_frames, part, desc = WORKLOADS[wl]
+    rows, row0, full_h, width, octs, my_frames = rank_geometry(pkg, wl, world, rank)
+    mode = pkg.MODE_REF if mode_name == "ref" else pkg.MODE_CONV
+    outputs = pkg.OUT_ALL if outputs_name == "all" else pkg.OUT_INPLACE
+    d_steps, d_warm = DEFAULT_STEPS[wl]
+    steps = steps if steps is not None else d_steps
+    warmup = max(warmup if warmup is not None else d_warm, 3)
 
     stream = torch.cuda.current_stream()
     probe = pkg.ScaleSpace(rows, width, octs, S, mode=mode, outputs=outputs, frames=1, device=local,
@@ -238,55 +252,58 @@ def run_native(args) -> dict:
         probe.close()
     # ring of frame slots: every step touches different HBM than the last few (L2 flush by rotation)
     slots = max(2, min(8, -(-(4 * L2_BYTES) // max(frame_bytes, 1)))) if rows else 0
-    if args.workload == "c5":
+    if wl == "c5":
         slots = 2
-    if args.mode == "conv" and part == "batch":
+    if wl == "c1":
+        slots = 64                                # two 32-frame batches: 2 x 32 x 16.4 MB = 1 GB ring
+    if mode_name == "conv" and part == "batch":
         slots = 8                                 # CONV launches one kernel per LEVEL for all slots of a batch call
-    if args.mode == "conv" and part == "rowband" and world > 1:
+    if mode_name == "conv" and part == "rowband" and world > 1:
         slots = 3                                 # CONV row bands keep up to 3 builds in flight (frame lanes, per-slot counters)
-    if args.mode == "conv" and part == "replica":
-        slots = 8                                 # CONV keeps up to 8 single-frame builds in flight (frame lanes)
-    if args.slots > 0:
-        slots = args.slots
+    if mode_name == "conv" and part == "replica":
+        slots = 8 if wl != "c1" else 64           # CONV keeps up to 8 single-frame builds in flight (frame lanes)
+    if slots_arg > 0:
+        slots = slots_arg
     ss = None
     if rows:
         ss = pkg.ScaleSpace(rows, width, octs, S, mode=mode, outputs=outputs, frames=slots, device=local,
                             band_row0=row0, full_height=full_h)
         ss.set_stream(stream.cuda_stream)
-        if args.tune:
-            ss.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in args.tune.split(",") if kv)})
+        if tune:
+            ss.set_tuning(**{k: int(v) for k, v in (kv.split("=") for kv in tune.split(",") if kv)})
         for s in range(slots):   # distinct synthetic frames, resident in HBM before the timed region
-            ss.upload(pkg.synth.noise(rows, width, frame=rank * 1000 + s, row0=row0), frame=s)
+            ss.upload(synth_frame(pkg, rows, width, rank * 1000 + s, row0), frame=s)
         ss.sync()
 
     launches = [0]
     dominant = [0]                                # launches of the dominant kernel (REF: the fused build kernel)
     cursor = [0]
     exchanger = None
-    if ss is not None and args.mode == "conv" and part == "rowband" and world > 1:
-        exchanger = (pkg.PeerExchanger(ss, rank, world) if args.halo == "peer"
+    if ss is not None and mode_name == "conv" and part == "rowband" and world > 1:
+        exchanger = (pkg.PeerExchanger(ss, rank, world) if halo == "peer"
                      else pkg.DistExchanger(ss, rank, world, torch.device("cuda", local)))
+    conv_launches = ss.levels + (ss.levels - 1) * (ss.octaves - 1) if ss is not None else 0
+    batch_cap = 32 if wl == "c1" else slots       # frames per library call
 
     def step():
         """One pass over this rank's share of the batch: my_frames frames through the slot ring."""
         if ss is None:
             return
-        if exchanger is not None:            # CONV row bands: per-level neighbour halo exchange over NCCL P2P
+        if exchanger is not None:            # CONV row bands: halos over NVLink peer memory (or NCCL P2P per level)
             exchanger.build(cursor[0])
-            launches[0] += conv_launches if args.halo == "nccl" else ss.last_launches()
+            launches[0] += conv_launches if halo == "nccl" else ss.last_launches()
             dominant[0] += conv_launches
             cursor[0] = (cursor[0] + 1) % slots
             return
         left = my_frames
         while left:
-            n = min(left, slots - cursor[0])
+            n = min(left, slots - cursor[0], batch_cap)
             ss.build_batch(cursor[0], n)
             launches[0] += ss.last_launches()
-            dominant[0] += 1 if args.mode == "ref" else conv_launches
+            dominant[0] += 1 if mode_name == "ref" else conv_launches
             cursor[0] = (cursor[0] + n) % slots
             left -= n
 
-    conv_launches = ss.levels + (ss.levels - 1) * (ss.octaves - 1) if ss is not None else 0
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -303,6 +320,8 @@ def run_native(args) -> dict:
     torch.cuda.synchronize()
     sampler.active(False)
     dist.barrier()
+    if ss is not None:
+        ss.sync()                                # surfaces a timed-out neighbour / level wait as an error, not as a number
     my_ms = ev0.elapsed_time(ev1)
     my_launches = launches[0]                    # kernels launched inside the timed region
     my_dominant = dominant[0]
@@ -312,10 +331,10 @@ def run_native(args) -> dict:
     # Second, short pass with a CUDA event pair around EVERY step: median / min per step.  Event records between
     # launches keep consecutive frames from overlapping, so this is the isolated-step figure, not the throughput.
     per_step = None
-    if ss is not None:
-        if args.mode == "conv":                  # one build at a time: no frame lanes for the isolated-step figure
+    if ss is not None and per_step_pass and exchanger is None:
+        if mode_name == "conv":                  # one build at a time: no frame lanes for the isolated-step figure
             ss.set_tuning(conv_lanes=1)
-            for _ in range(2 * slots + 2):       # (retuning drops the captured launch sequences: warm them up again)
+            for _ in range(min(2 * slots + 2, 12)):   # (retuning drops the captured launch sequences: warm them up again)
                 step()
             torch.cuda.synchronize()
         n_ev = max(5, min(50, steps))
@@ -330,41 +349,37 @@ def run_native(args) -> dict:
                     "note": "isolated steps (event pair per step, no overlap between consecutive frames)"}
     px_per_step_all = float(H) * W * (total_frames if part != "replica" else total_frames * world)
     value = px_per_step_all / (ms_per_step * 1e-3) / 1e6                      # Mpix/s, whole job
-    # roofline of the dominant (only) kernel on this rank: algorithmic bytes per launch / mean launch time
+    # Roofline: ALGORITHMIC bytes (B_full: the input read once + every output plane written once) per
+    # launch of the dominant kernel / its mean duration.  REF: one fused launch per batch call.  CONV: one strip-kernel
+    # launch per level, so bytes/launch = B_full / launches per frame; the intermediate re-reads of the per-level
+    # schedule (12 B per level-pixel) are NOT algorithmic bytes and show up as a lower fraction, with the design-traffic
+    # fraction reported next to it as `per_level_frac`.
     peak, peak_src = measured_peak()
-    work_bytes = frame_bytes
-    if args.mode == "conv" and ss is not None:
-        # per-level design traffic: every level kernel reads its input plane once and writes G_s (+ DoG_{s-1},
-        # + the decimated base of the next octave): 12 B per level-pixel, vs B_full's 4*(2S+5) per octave pixel
+    bytes_per_launch = frame_bytes * my_frames * steps / max(my_dominant, 1)
+    launch_ms = my_ms / max(my_dominant, 1)
+    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if my_dominant else 0.0
+    achieved = dist.sum(achieved) / world                                      # mean per-GPU achieved GB/s
+    per_level_frac = None
+    if mode_name == "conv" and ss is not None:
         px = [ss.level_dims(o)[0] * ss.level_dims(o)[1] for o in range(ss.octaves)]
         nl = ss.levels
         work_bytes = rows * width * (1 if ss.pixel_type == pkg.PIXEL_U8 else 4) + 4 * px[0] * (nl + nl - 1 + nl - 1)
         for o in range(1, ss.octaves):
             work_bytes += 4 * px[o] * (1 + (nl - 1) * 3)
-    bytes_per_launch = work_bytes * my_frames * steps / max(my_dominant, 1)
-    launch_ms = my_ms / max(my_dominant, 1)
-    achieved = bytes_per_launch / (launch_ms * 1e-3) / 1e9 if my_dominant else 0.0
-    achieved = dist.sum(achieved) / world                                      # mean per-GPU achieved GB/s
-    traffic = ncu_traffic(args.workload if args.mode == "ref" else "conv:" + args.workload)
-
-    # ---- end to end through the C ABI with HOST buffers ----------------------------------------------
-    e2e = None
-    if not args.no_e2e and ss is not None:
-        e2e = run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my_frames, local, rank,
-                      px_per_step_all, mode)
-    clocks = sampler.finish()
-
+        per_level_frac = round(work_bytes * my_frames * steps / (my_ms * 1e-3) / 1e9 / peak, 4) if my_ms else None
+    traffic = ncu_traffic(wl if mode_name == "ref" else "conv:" + wl)
     out = {
-        "metric": METRIC, "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world, "steps": steps,
-        "warmup": warmup, "ms_per_step": round(ms_per_step, 6), "higher_is_better": True,
-        "scaling": "weak" if part == "replica" else "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic (splitmix64 noise frames, int32 pixels 0..255, resident in HBM before timing)",
-        "config": {"workload": desc, "name": args.workload, "mode": args.mode.upper(), "S": S, "octaves": octs,
-                   "outputs": "S+3 Gaussian + S+2 DoG planes (B_full)" if args.outputs == "all"
+        "value": round(value, 1), "unit": "Mpix/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": round(ms_per_step, 6), "scaling": "weak" if part == "replica" else "strong",
+        "config": {"workload": desc, "name": wl, "mode": mode_name.upper(), "S": S, "octaves": octs,
+                   "outputs": "S+3 Gaussian + S+2 DoG planes (B_full)" if outputs_name == "all"
                    else "reference in-place layout: S+2 DoG + top Gaussian (B_ref)",
                    "partition": part if world > 1 else "single GPU", "frame_slots": slots,
+                   **({"halo": "neighbour planes read inside the blur kernel over NVLink peer memory (CUDA IPC), per-segment "
+                               "counters, one CUDA graph per build" if halo == "peer" else "NCCL P2P per level"}
+                      if exchanger is not None else {}),
                    **({"frames_in_flight": "up to %d single-frame builds overlap (frame lanes, one stream set each)" % min(8, slots)}
-                      if args.mode == "conv" and part == "replica" else {}),
+                      if mode_name == "conv" and part == "replica" else {}),
                    "l2": f"ring of {slots} frame slots = {slots * frame_bytes / 1e6:.0f} MB > {L2_BYTES >> 20} MB L2; "
                          "consecutive steps touch different HBM"},
         "gpu_launches": int(dist.sum(my_launches)),
@@ -372,22 +387,190 @@ def run_native(args) -> dict:
                      "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                      "frac_of_nominal_8000": round(achieved / 8000.0, 4),     # north_star's "~8 TB/s" figure, for reference
                      "algorithmic_bytes_per_launch": int(bytes_per_launch), "launch_us": round(launch_ms * 1e3, 3),
-                     "kernel": "sspyr::ref_fused_kernel" if args.mode == "ref" else "sspyr::conv_strip_kernel (one launch per level)",
-                     "bytes_model": "B_full: input read once + every output plane written once" if args.mode == "ref"
-                     else "per-level: input plane read + G_s, DoG_{s-1}, decimated base written, summed over the level launches",
-                     "b_full_frac": round(frame_bytes * my_frames * steps / (my_ms * 1e-3) / 1e9 / peak, 4) if my_ms else None},
-        "clocks": clocks,
+                     "kernel": "sspyr::ref_fused_kernel" if mode_name == "ref" else "sspyr::conv_strip_kernel (one launch per level)",
+                     "bytes_model": "B_full: input read once + every output plane written once (SURVEY 8d)",
+                     **({"per_level_frac": per_level_frac,
+                         "per_level_note": "same time against the per-level design traffic (12 B per level-pixel): what the "
+                                           "one-launch-per-level schedule can reach at best"} if per_level_frac is not None else {})},
     }
     if per_step:
         out["per_step_events"] = per_step
-    if e2e:
-        out["e2e"] = e2e
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
+    out["_geom"] = (rows, row0, full_h, width, octs, my_frames, px_per_step_all, mode)
     if ss:
         ss.close()
+    return out
+
+
+def run_native(args) -> dict:
+    import torch
+
+    rank, world, local = dist_env()
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run --nproc-per-node N (one rank per GPU)")
+    torch.cuda.set_device(local)
+    topo = bind_to_gpu_numa_node(local)          # before any pinned allocation: first touch on the GPU's node
+    dist = Dist(world, local)
+    pkg = entry.load_package()
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    rec = measure(pkg, torch, dist, sampler, args.workload, args.mode, args.outputs, world, rank, local,
+                  args.steps, args.warmup, args.halo, args.tune, args.slots)
+    rows, row0, full_h, width, octs, my_frames, px_per_step_all, mode = rec.pop("_geom")
+    part = WORKLOADS[args.workload][4]
+
+    # ---- end to end through the C ABI with HOST buffers ----------------------------------------------
+    e2e = None
+    banded_conv = args.mode == "conv" and part == "rowband" and world > 1     # (driven through PeerExchanger: no e2e leg)
+    if not args.no_e2e and rows and not banded_conv:
+        e2e = run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my_frames, local, rank,
+                      px_per_step_all, mode)
+        e2e["host"] = topo
+    out = {"metric": METRIC, "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": world,
+           "steps": rec.pop("steps"), "warmup": rec.pop("warmup"), "ms_per_step": rec.pop("ms_per_step"),
+           "higher_is_better": True, "scaling": rec.pop("scaling"), "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic (splitmix64 noise frames, int32 pixels 0..255, resident in HBM before timing)"}
+    rec.pop("n_gpus")
+    out.update(rec)
+    if e2e:
+        out["e2e"] = e2e
+    if rank == 0 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
+    dist.barrier()
+
+    # ---- extras: the other sharded workloads / CONV mode, bounded, same process group -------------------
+    default_run = args.mode == "ref" and args.workload == "c3" and args.outputs == "all" and not args.tune
+    if (default_run or args.extras) and not args.no_extras:
+        out["extras"] = run_extras(pkg, torch, dist, sampler, args, world, rank, local)
+    out["clocks"] = sampler.finish()
     dist.close()
     return out if rank == 0 else {}
+
+
+class Solo:
+    """The Dist interface for a measurement that only one rank of a larger job takes part in."""
+    world = 1
+
+    def barrier(self):
+        pass
+
+    def max(self, v):
+        return v
+
+    def sum(self, v):
+        return v
+
+
+EXTRAS_N1 = [  # (key, workload, mode, steps, warmup, e2e)
+    ("c2_ref", "c2", "ref", 500, 20, True),
+    ("c2_conv", "c2", "conv", 300, 20, True),
+    ("c1_ref", "c1", "ref", 200, 10, False),
+    ("c3_conv", "c3", "conv", 2, 3, False),
+    ("c4_ref", "c4", "ref", 100, 5, False),
+    ("c4_conv", "c4", "conv", 50, 5, False),
+    ("c5_ref", "c5", "ref", 10, 3, False),
+    ("c5_conv", "c5", "conv", 8, 3, False),
+]
+EXTRAS_NX = [  # sharded workloads: measured on all ranks, then on rank 0 alone (`n1`) for the speed-up
+    ("c4_ref_rowband", "c4", "ref", 100, 5),
+    ("c4_conv_rowband", "c4", "conv", 50, 5),
+    ("c5_conv_rowband", "c5", "conv", 10, 3),
+    ("c3_conv_batch", "c3", "conv", 2, 3),
+]
+
+
+def run_extras(pkg, torch, dist, sampler, args, world, rank, local) -> dict:
+    """Bounded extra records.  A failure in one of them is reported in place and never breaks the main line."""
+    want = [k for k in args.extras.split(",") if k] if args.extras else None
+    res = {}
+    keep = ("value", "unit", "ms_per_step", "steps", "scaling", "gpu_launches", "config", "per_step_events", "roofline")
+
+    def slim(r):
+        r.pop("_geom", None)
+        return {k: r[k] for k in keep if k in r}
+
+    if world == 1:
+        for key, wl, mode, steps, warm, with_e2e in EXTRAS_N1:
+            if want is not None and key not in want:
+                continue
+            try:
+                t0 = time.perf_counter()
+                r = measure(pkg, torch, dist, sampler, wl, mode, "all", 1, 0, local, steps, warm)
+                rows, row0, full_h, width, octs, my_frames, px_all, m = r["_geom"]
+                rec = slim(r)
+                if with_e2e and not args.no_e2e:
+                    sub = argparse.Namespace(**{**vars(args), "workload": wl, "mode": mode, "steps": 30})
+                    rec["e2e"] = run_e2e(pkg, torch, dist, sampler, sub, rows, row0, full_h, width, octs, my_frames, local, 0,
+                                         px_all, m)
+                if mode == "conv" and wl == "c2" and not args.no_cpu_baseline:
+                    rec["cpu_baseline"] = cpu_baseline_conv(wl, budget_s=8.0)
+                rec["wall_s"] = round(time.perf_counter() - t0, 1)
+                res[key] = rec
+            except Exception as e:
+                res[key] = {"unavailable": repr(e)[:300]}
+                torch.cuda.synchronize()
+        return res
+    for key, wl, mode, steps, warm in EXTRAS_NX:
+        if want is not None and key not in want:
+            continue
+        try:
+            t0 = time.perf_counter()
+            r = measure(pkg, torch, dist, sampler, wl, mode, "all", world, rank, local, steps, warm, halo=args.halo,
+                        per_step_pass=False)
+            rec = slim(r)
+            dist.barrier()
+            n1 = None
+            if rank == 0:                         # the same workload on ONE GPU, same run, same box: the speed-up's denominator
+                r1 = measure(pkg, torch, Solo(), sampler, wl, mode, "all", 1, 0, local, max(2, steps // 2), warm,
+                             per_step_pass=False)
+                n1 = {"value": r1["value"], "ms_per_step": r1["ms_per_step"], "steps": r1["steps"],
+                      "roofline_frac": r1["roofline"]["frac"]}
+            dist.barrier()
+            if n1:
+                rec["n1"] = n1
+                rec["speedup_vs_n1"] = round(rec["value"] / n1["value"], 3)
+                rec["efficiency_vs_n1"] = round(rec["value"] / n1["value"] / world, 3)
+            rec["wall_s"] = round(time.perf_counter() - t0, 1)
+            res[key] = rec
+        except Exception as e:
+            res[key] = {"unavailable": repr(e)[:300]}
+            try:
+                torch.cuda.synchronize()
+                dist.barrier()
+            except Exception:
+                break
+    return res
+
+
+def bind_to_gpu_numa_node(local: int) -> dict:
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node before any pinned buffer is allocated (pinned
+    pages are placed on the allocating thread's node).  Reports what was found; never fails the run."""
+    info = {"numa_node": None, "cpus_bound": None}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local), "pci_device_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        info["numa_node"] = node
+        allowed = os.sched_getaffinity(0)
+        info["cpus_allowed"] = len(allowed)
+        if node >= 0:
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus &= allowed
+            if cpus and cpus != allowed:
+                os.sched_setaffinity(0, cpus)
+                info["cpus_bound"] = len(cpus)
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["numa_nodes_on_host"] = len(nodes)
+    except Exception as e:
+        info["note"] = repr(e)[:120]
+    return info
 
 
 def run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my_frames, local, rank,

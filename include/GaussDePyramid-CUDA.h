@@ -37,55 +37,65 @@ class GaussPyramid_cuda {
 public:
     int** data;  // image grey values, as in the reference (public, caller may edit then call GaussPyInit())
     GaussPyramid_cuda() : data(nullptr), GaussPy(nullptr), initialized(false), length(0), S(0), layer(0),
-                          filter(nullptr), h_(nullptr), mirror_(nullptr), staging_(nullptr), download_(true) {}
+                          filter(nullptr), h_(nullptr), mirror_(nullptr), staging_(nullptr), download_(true),
+                          rows_(0), cols_(0), float_pixels_(false), mode_(SSPYR_MODE_REF), state_(NOTHING) {}
 
+    // The reference's constructor (GuassDePyramid.h:36-58): square int image, all octaves, sigma 2.0.
     GaussPyramid_cuda(int** img, int len, int S_) : GaussPyramid_cuda() {
-        length = len;
+        length = rows_ = cols_ = len;
         S = S_;
-        data = new int*[len];                                   // GuassDePyramid.h:38-46
+        data = new int*[len]();                                 // GuassDePyramid.h:38-46
         for (int i = 0; i < len; ++i) {
             data[i] = new int[len];
             std::memcpy(data[i], img[i], sizeof(int) * (size_t)len);
         }
-        sspyr_config cfg;
-        sspyr_default_config(&cfg);
-        cfg.height = cfg.width = len;
-        cfg.S = S;
-        cfg.octaves = 0;                                        // all: floor(log2 len)+1, :48-53
-        cfg.outputs = SSPYR_OUT_ALL;
-        check(sspyr_create(&cfg, &h_), "sspyr_create");
-        check(sspyr_set_tuning(h_, "timing", 1), "sspyr_set_tuning");   // last_device_ms() for the driver's report
-        layer = sspyr_num_octaves(h_);
-        // pinned host mirror in the reference's dense in-place order + its float**** row tables
-        size_t floats = 0;
-        for (int o = 0; o < layer; ++o) floats += (size_t)(S + 3) * side(o) * side(o);
-        check(sspyr_host_alloc(sizeof(float) * (floats ? floats : 1), (void**)&mirror_), "sspyr_host_alloc");
-        check(sspyr_host_alloc(sizeof(int) * (size_t)len * len, (void**)&staging_), "sspyr_host_alloc");
-        GaussPy = new float***[layer];                          // :55
-        float* p = mirror_;
-        for (int o = 0; o < layer; ++o) {
-            GaussPy[o] = new float**[S + 3];
-            for (int s = 0; s < S + 3; ++s) {
-                GaussPy[o][s] = new float*[side(o)];
-                for (int r = 0; r < side(o); ++r, p += side(o)) GaussPy[o][s][r] = p;
-            }
-        }
+        setup(0, 0.0f);
         GaussPyInit();                                          // :57
+    }
+
+    // Superset constructor: a dense row-major H x W float image, a chosen octave count
+    // (0 = all), S, sigma0 (<= 0: the mode's default) and the mode (SSPYR_MODE_REF: the reference's pointwise window;
+    // SSPYR_MODE_CONV: the separable blur chain).  `data` stays null: the float pixels are kept in a private copy,
+    // reachable through pixels() -- edit them there, then call GaussPyInit() as with the reference's `data`.
+    GaussPyramid_cuda(const float* img, int H, int W, int octaves, int S_, float sigma0 = 0.0f, int mode = SSPYR_MODE_REF)
+        : GaussPyramid_cuda() {
+        rows_ = H;
+        cols_ = W;
+        length = H < W ? H : W;
+        S = S_;
+        float_pixels_ = true;
+        mode_ = mode;
+        setup(octaves, sigma0);
+        std::memcpy(staging_, img, sizeof(float) * (size_t)H * W);
+        GaussPyInit();
     }
 
     // K0 (GuassDePyramid.h:60-87): re-read `data`, upload, every level := decimated original.
     void GaussPyInit() {
-        for (int i = 0; i < length; ++i) std::memcpy(staging_ + (size_t)i * length, data[i], sizeof(int) * (size_t)length);
+        check(sspyr_sync(h_), "sspyr_sync");                    // an earlier asynchronous upload may still be reading staging_
+        if (!float_pixels_)
+            for (int i = 0; i < rows_; ++i)
+                std::memcpy(static_cast<int*>(staging_) + (size_t)i * cols_, data[i], sizeof(int) * (size_t)cols_);
         check(sspyr_upload(h_, 0, staging_, 0), "sspyr_upload");
-        check(sspyr_build_stage(h_, 0, SSPYR_STAGE_INIT), "sspyr_build_stage");
-        if (download_) { check(sspyr_download_gauss(h_, 0, mirror_), "sspyr_download_gauss"); check(sspyr_sync(h_), "sspyr_sync"); }
+        state_ = NOTHING;
+        if (mode_ == SSPYR_MODE_REF) {                          // (the blur chain has no "levels = decimated original" state)
+            check(sspyr_build_stage(h_, 0, SSPYR_STAGE_INIT), "sspyr_build_stage");
+            state_ = INIT;
+            if (download_) { check(sspyr_download_gauss(h_, 0, mirror_), "sspyr_download_gauss"); check(sspyr_sync(h_), "sspyr_sync"); }
+        }
         initialized = true;
     }
 
-    // GuassDePyramid.h:106-134: the S+3 window-multiplied levels of octave `theLayer`.
+    // GuassDePyramid.h:106-134: the S+3 filtered levels of octave `theLayer`.  The device builds all octaves in one
+    // fused pass; that pass runs once and is reused until the next GaussPyInit()/GenerateDoG(), so the reference's
+    // `for (o...) GaussFilter(o)` idiom costs ONE build plus one download per octave.
     void GaussFilter(int theLayer) {
         if (theLayer < 0 || theLayer >= layer) throw std::out_of_range("GaussFilter: theLayer");
-        check(sspyr_build_stage(h_, 0, SSPYR_STAGE_FILTER), "sspyr_build_stage");
+        if (state_ != FILTERED) {                               // (a full build also leaves every Gaussian level in place)
+            if (mode_ == SSPYR_MODE_REF) check(sspyr_build_stage(h_, 0, SSPYR_STAGE_FILTER), "sspyr_build_stage");
+            else check(sspyr_build(h_, 0), "sspyr_build");      // CONV: the Gaussian levels are outputs of the full build
+            state_ = FILTERED;
+        }
         for (int s = 0; s < S + 3; ++s)
             check(sspyr_download(h_, 0, theLayer, s, SSPYR_KIND_GAUSS, GaussPy[theLayer][s][0], 0), "sspyr_download");
     }
@@ -93,6 +103,7 @@ public:
     // GuassDePyramid.h:136-149: the whole pipeline, fused on the GPU.
     void GenerateDoG() {
         check(sspyr_build(h_, 0), "sspyr_build");
+        state_ = FILTERED;
         if (download_) check(sspyr_download_inplace(h_, 0, mirror_), "sspyr_download_inplace");
         check(sspyr_sync(h_), "sspyr_sync");
     }
@@ -113,26 +124,26 @@ public:
     // GuassDePyramid.h:89-104: level 0 of every octave, one text row per image row, a ruler of "==" per octave.
     void output() {
         for (int o = 0; o < layer; ++o) {
-            const int n = side(o);
-            for (int r = 0; r < n; ++r) {
+            for (int r = 0; r < rows(o); ++r) {
                 const float* row = GaussPy[o][0][r];
-                for (int c = 0; c < n; ++c) std::cout << row[c] << " ";
+                for (int c = 0; c < cols(o); ++c) std::cout << row[c] << " ";
                 std::cout << std::endl;
             }
-            std::cout << std::string(2 * (size_t)n, '=') << std::endl;
+            std::cout << std::string(2 * (size_t)cols(o), '=') << std::endl;
         }
     }
 
     ~GaussPyramid_cuda() {                                      // GuassDePyramid.h:151-170 (and frees `data`)
         if (GaussPy) {
             for (int o = 0; o < layer; ++o) {
-                for (int s = 0; s < S + 3; ++s) delete[] GaussPy[o][s];
+                if (!GaussPy[o]) continue;                      // (tables are value-initialised: a constructor that threw half-way
+                for (int s = 0; s < S + 3; ++s) delete[] GaussPy[o][s];   //  leaves null entries, never garbage)
                 delete[] GaussPy[o];
             }
             delete[] GaussPy;
         }
         if (data) {
-            for (int i = 0; i < length; ++i) delete[] data[i];
+            for (int i = 0; i < rows_; ++i) delete[] data[i];
             delete[] data;
         }
         if (mirror_) sspyr_host_free(mirror_);
@@ -146,6 +157,9 @@ public:
     // ---- additions (not in the reference) ----
     int octaves() const { return layer; }
     int side(int o) const { return length >> o; }
+    int rows(int o) const { return rows_ >> o; }
+    int cols(int o) const { return cols_ >> o; }
+    float* pixels() { return float_pixels_ ? static_cast<float*>(staging_) : nullptr; }   // superset ctor: the image copy
     float last_device_ms() { float ms = 0; check(sspyr_elapsed_ms(h_, &ms), "sspyr_elapsed_ms"); return ms; }
     void set_download(bool on) { download_ = on; }   // false: results stay on the device (kernel-only timing)
     sspyr_handle handle() const { return h_; }
@@ -160,13 +174,47 @@ protected:
     float* filter;  // kept for layout familiarity; the window tables live on the device
 
 private:
+    enum State { NOTHING, INIT, FILTERED };   // what the Gaussian-level planes of slot 0 hold on the device
     void check(int rc, const char* what) {
         if (rc < 0) throw std::runtime_error(std::string(what) + ": " + sspyr_last_error(h_));
     }
+    // handle + pinned host mirror in the reference's dense in-place order + its float**** row tables (:55, :62-72)
+    void setup(int octaves, float sigma0) {
+        sspyr_config cfg;
+        sspyr_default_config(&cfg);
+        cfg.height = rows_;
+        cfg.width = cols_;
+        cfg.S = S;
+        cfg.octaves = octaves;                                  // 0 = all: floor(log2 len)+1, :48-53
+        cfg.outputs = SSPYR_OUT_ALL;
+        cfg.mode = mode_;
+        cfg.sigma0 = sigma0;
+        cfg.pixel_type = float_pixels_ ? SSPYR_PIXEL_F32 : SSPYR_PIXEL_I32;
+        check(sspyr_create(&cfg, &h_), "sspyr_create");
+        check(sspyr_set_tuning(h_, "timing", 1), "sspyr_set_tuning");   // last_device_ms() for the driver's report
+        layer = sspyr_num_octaves(h_);
+        size_t floats = 0;
+        for (int o = 0; o < layer; ++o) floats += (size_t)(S + 3) * rows(o) * cols(o);
+        check(sspyr_host_alloc(sizeof(float) * (floats ? floats : 1), (void**)&mirror_), "sspyr_host_alloc");
+        check(sspyr_host_alloc(4 * (size_t)rows_ * cols_, &staging_), "sspyr_host_alloc");
+        GaussPy = new float***[layer]();                        // :55 (value-initialised)
+        float* p = mirror_;
+        for (int o = 0; o < layer; ++o) {
+            GaussPy[o] = new float**[S + 3]();
+            for (int s = 0; s < S + 3; ++s) {
+                GaussPy[o][s] = new float*[rows(o)];
+                for (int r = 0; r < rows(o); ++r, p += cols(o)) GaussPy[o][s][r] = p;
+            }
+        }
+    }
     sspyr_handle h_;
     float* mirror_;
-    int* staging_;
+    void* staging_;   // pinned: int pixels (reference constructor) or float pixels (superset constructor)
     bool download_;
+    int rows_, cols_;
+    bool float_pixels_;
+    int mode_;
+    State state_;
 };
 
 #endif  // SIFT_GUASS_NORMAL_GAUSSDEPYRAMID_CUDA_H

@@ -107,7 +107,8 @@ template <int SRC>
 __device__ __forceinline__ float load_src(const void* __restrict__ base, size_t idx) {
     if constexpr (SRC == SSPYR_PIXEL_I32) return (float)__ldg(static_cast<const int*>(base) + idx);
     else if constexpr (SRC == SSPYR_PIXEL_U8) return (float)__ldg(static_cast<const unsigned char*>(base) + idx);
-    else return __ldg(static_cast<const float*>(base) + idx);
+    else if constexpr (SRC == CONV_SRC_PLANE) return __ldcg(static_cast<const float*>(base) + idx);   // written by a grid that may
+    else return __ldg(static_cast<const float*>(base) + idx);                                         // still run (chained levels): no .nc
 }
 
 // Stage one tile (centre + halo) of frame fz into sIn: clamp to edge, or the neighbour's halo rows for a band.
@@ -159,7 +160,7 @@ __device__ __forceinline__ void conv_stage_tile(const ConvParams& P, float* __re
         } else {
             for (int lx = lane; lx < COLS; lx += 32) {
                 const int gx = min(max(x0 - RA + lx, 0), P.W - 1);
-                srow[lx] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(row, (size_t)gx);
+                srow[lx] = load_src<SRC>(row, (size_t)gx);
             }
         }
     }

@@ -130,7 +130,7 @@ __device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __r
         } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                s[i] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(row, (size_t)min(max(gx + i, 0), P.W - 1));
+                s[i] = load_src<SRC>(row, (size_t)min(max(gx + i, 0), P.W - 1));
         }
     }
 }
@@ -310,12 +310,13 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     strip_stage_rows<R, SRC, 2 * R>(P, scratch, y_begin - R, x0, src, tid);
     stage_step(y_begin + R);
     __pipeline_wait_prior(0);
-    if (pending_tma) {
-        if (!mbar_wait(&bar, phase)) return;
+    bool lost = false;                                   // a TMA load never completed (bounded wait): flag it, skip the work,
+    if (pending_tma) {                                   // but still publish the counters so that nobody waits on this CTA
+        if (!mbar_wait(&bar, phase)) lost = true;
         phase ^= 1;
     }
-    __syncthreads();
-    strip_row_pass<R, 2 * R, 0>(P, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
+    lost = __syncthreads_or(lost);                       // (CTA-uniform: threads time out individually)
+    if (!lost) strip_row_pass<R, 2 * R, 0>(P, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
 
     const int cq = tid % TPB, rb = tid / TPB;           // column group / row block of the column pass
     const int x = x0 + cq * PX;
@@ -330,16 +331,17 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     [[maybe_unused]] float* gq = g + (size_t)(y_begin + rb * PY) * P.dst_pitch + x;
     [[maybe_unused]] float* dq = d ? d + (size_t)(y_begin + rb * PY) * P.dst_pitch + x : nullptr;
 #pragma unroll 1
-    for (int k = 0; k < nsteps; ++k) {
+    for (int k = 0; k < nsteps && !lost; ++k) {
+        bool miss = false;
         if (k > 0) {                                     // (step 0 was awaited in the prologue)
             if (pending_tma) {
-                if (!mbar_wait(&bar, phase)) return;     // (bounded; never observed)
+                miss = !mbar_wait(&bar, phase);          // (bounded; never observed)
                 phase ^= 1;
             } else {
                 __pipeline_wait_prior(0);
             }
         }
-        __syncthreads();                                 // new rows landed; carried rows are in place; scratch is free
+        if (__syncthreads_or(miss)) { lost = true; break; }   // new rows landed; carried rows are in place; scratch is free
         strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
 
         // ---- centre values for DoG_{s-1} = G_{s-1} - G_s: input rows yr .. yr+PY-1 of this thread's quad ----
@@ -372,6 +374,9 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                         } else if constexpr (SRC == SSPYR_PIXEL_U8) {
                             const uchar4 t = __ldg(reinterpret_cast<const uchar4*>(crow + x));
                             cen[j][0] = (float)t.x; cen[j][1] = (float)t.y; cen[j][2] = (float)t.z; cen[j][3] = (float)t.w;
+                        } else if constexpr (SRC == CONV_SRC_PLANE) {   // the producing grid may still be running: coherent load
+                            const float4 t = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
+                            cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
                         } else {
                             const float4 t = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(crow) + x));
                             cen[j][0] = t.x; cen[j][1] = t.y; cen[j][2] = t.z; cen[j][3] = t.w;
@@ -379,7 +384,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                     } else {
 #pragma unroll
                         for (int i = 0; i < PX; ++i)
-                            cen[j][i] = load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(crow, (size_t)(x + i));
+                            cen[j][i] = load_src<SRC>(crow, (size_t)(x + i));
                     }
                 }
             }
@@ -489,7 +494,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                 for (int i = 0; i < PX; ++i)
                     if (i < nvalid) {
                         g[o + i] = acc[j][i];
-                        if (d) __stcs(d + o + i, load_src<SRC == CONV_SRC_PLANE ? SSPYR_PIXEL_F32 : SRC>(crow, (size_t)(x + i)) - acc[j][i]);
+                        if (d) __stcs(d + o + i, load_src<SRC>(crow, (size_t)(x + i)) - acc[j][i]);
                     }
                 if (dec && (y & 1) == 0) {
                     const int dy = y >> 1, dx = x >> 1;
@@ -522,6 +527,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             }
         }
     }
+    if (lost && P.timeout_mark && tid == 0) *P.timeout_mark = 0xC0000000u | (unsigned)blockIdx.x;   // surfaces in sspyr_sync
     // Level chaining: this (strip, segment) is written -- count the build for the next level's CTAs.
     if (P.seg_pub) {
         __syncthreads();

@@ -90,7 +90,11 @@ cudaError_t launch_ref(sspyr_ctx* h, int first, int count, int outputs, int* lau
         for (int k = 0; k < n; ++k)
             for (int q = 0; q < h->last_count; ++q)
                 clash |= ((f0 + k) % frames) == ((h->last_first + q) % frames);
-        const bool pdl = h->tune.pdl != 0 && !clash;
+        // A slot that reads a caller-produced device image (sspyr_set_input_device), or any build once raw device
+        // pointers are in the caller's hands (strict_order), is launched WITHOUT the PDL attribute: the kernel reads
+        // its whole input before its griddepcontrol.wait, and under PDL it could be scheduled at the producer's
+        // implicit trigger, before the producer's stores are guaranteed visible.
+        const bool pdl = h->tune.pdl != 0 && !clash && !h->ext_in[f0] && !h->strict_order;
         h->last_first = f0;
         h->last_count = n;
 

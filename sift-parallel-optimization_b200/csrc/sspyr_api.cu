@@ -236,6 +236,9 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
     }
     if ((cfg.outputs & SSPYR_OUT_EXTREMA) && !(cfg.outputs & SSPYR_OUT_DOG))
         return fail(nullptr, SSPYR_ERR_ARG, "SSPYR_OUT_EXTREMA needs SSPYR_OUT_DOG");
+    if ((cfg.outputs & SSPYR_OUT_EXTREMA) && banded)         // the scan treats the handle's first/last row as the image border
+        return fail(nullptr, SSPYR_ERR_UNSUPPORTED, "SSPYR_OUT_EXTREMA is not available on a row-band handle (band seams would be "
+                                                    "scanned as image borders); scan the bands' DoG planes with a whole-frame handle");
     if (cfg.mode == SSPYR_MODE_CONV) cfg.outputs |= SSPYR_OUT_GAUSS;   // the blur chain reads its own levels
 
     int ndev = 0;
@@ -565,7 +568,7 @@ int sspyr_sync(sspyr_handle h) {
     if (!h) return SSPYR_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (h->peer[0].attached || h->peer[1].attached || (h->d_seg && h->tune.conv_chain != 0)) {
+    if (h->cfg.mode == SSPYR_MODE_CONV) {                    // a bounded wait (neighbour band, previous level, TMA) gave up
         unsigned mark = 0;
         CU(h, cudaMemcpy(&mark, h->d_flag + 16, sizeof(mark), cudaMemcpyDeviceToHost));
         if (mark) {

@@ -247,6 +247,7 @@ class GaussPyramid:
         """GuassDePyramid.h:60-87 -- every level of every octave := decimated original (K0, on the GPU)."""
         self._ss.upload(self.data)      # `data` is public and may have been edited by the caller
         self._ss.build(stage=L.STAGE_INIT)
+        self._filtered = False
         self.GaussPy = [list(a) for a in self._ss.download_gauss()]
         self.initialized = True
 
@@ -254,12 +255,15 @@ class GaussPyramid:
         """GuassDePyramid.h:106-134 -- window-multiply all S+3 levels of octave `theLayer`."""
         if not 0 <= theLayer < self.layer:
             raise IndexError("theLayer out of range")
-        self._ss.build(stage=L.STAGE_FILTER)
+        if not self._filtered:          # one fused pass filters every octave; `for o: GaussFilter(o)` reuses it
+            self._ss.build(stage=L.STAGE_FILTER)
+            self._filtered = True
         self.GaussPy[theLayer] = [self._ss.download(theLayer, s, L.KIND_GAUSS) for s in range(self.S + 3)]
 
     def GenerateDoG(self) -> None:
         """GuassDePyramid.h:136-149 -- slots 0..S+1 become DoG_s = G_s - G_{s+1}; slot S+2 keeps G_{S+2}."""
         self._ss.build(stage=L.STAGE_DOG)
+        self._filtered = True           # (a full build leaves every Gaussian level in place too)
         self.GaussPy = [list(a) for a in self._ss.download_inplace()]
 
     def output(self, file=None) -> None:
