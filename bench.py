@@ -654,6 +654,9 @@ def square_equivalent(H: int, W: int) -> int:
     return n
 
 
+REF_SIDE_CAP = 2880      # largest square the CPU legs run: 2880^2 == 3840x2160 (c3); c4/c5 are sampled at this size
+
+
 def cpu_baseline(workload: str, budget_s: float = 12.0, threads: int = 1) -> dict:
     """Serial reference header (1 core) on a bounded sample of the workload: the GenerateDoG() region the
     reference itself times (main.cpp:67-69), levels reset by GaussPyInit() (untimed) before every rep."""
@@ -663,7 +666,7 @@ def cpu_baseline(workload: str, budget_s: float = 12.0, threads: int = 1) -> dic
     H, W, octs, frames, _, _ = WORKLOADS[workload]
     cores = os.cpu_count() or 1
     if O.have_ref():
-        n = min(square_equivalent(H, W), 2048)
+        n = min(square_equivalent(H, W), REF_SIDE_CAP)
         img = pkg_synth.noise(n, n)
         one = float(O.time_header_serial(img, S, 1, 1)[0])
         reps = int(max(3, min(200, budget_s * 1e3 / max(one, 1e-3))))
@@ -706,7 +709,7 @@ def run_reference(args) -> dict:
     cores = os.cpu_count() or 1
     variants = {}
     if O.have_ref():
-        n = min(square_equivalent(H, W), 2048)
+        n = min(square_equivalent(H, W), REF_SIDE_CAP)
         img = synth.noise(n, n)
         px = n * n
         ms = O.time_header_serial(img, S, min(warmup, 3), steps)
@@ -774,30 +777,31 @@ def run_reference(args) -> dict:
     }
 
 
-def conv_extra(args) -> dict:
-    """Supplementary figure for a default single-GPU run: the same workload in CONV mode (the true separable blur
-    of the north_star; no upstream parity), measured by a child process AFTER the main line's timed regions and
-    bounded by a time-out, so it can neither disturb nor block the REF measurement."""
-    import subprocess
-    try:
-        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", args.workload, "--mode", "conv", "--no-e2e",
-                            "--no-cpu-baseline", "--no-conv-extra"], capture_output=True, text=True, timeout=180)
-        d = json.loads(r.stdout.strip().splitlines()[-1])
-        return {"note": "same workload, CONV mode: separable Gaussian blur per level, DoG and 2x decimation in the blur epilogue "
-                        "(parity: own CPU specification within 1e-4 of full scale; the reference has no convolution)",
-                "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "steps": d["steps"],
-                "gpu_launches": d["gpu_launches"], "config": d["config"], "per_step_events": d.get("per_step_events"),
-                "roofline": {k: d["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "b_full_frac", "kernel", "bytes_model")}}
-    except Exception as e:  # a supplementary figure must never break the main line
-        return {"unavailable": repr(e)[:300]}
+def cpu_baseline_conv(workload: str, budget_s: float = 8.0) -> dict:
+    """CONV mode has no upstream CPU code (the reference's filter is pointwise): the CPU figure beside it is the
+    repo's own specification, oracle/sspyr_oracle.c orc_conv_build (double accumulation, OpenMP over rows), on every
+    host thread -- labelled as such."""
+    import numpy as np
+    O = entry.load_oracle()
+    synth = entry.load_package().synth
+    H, W, octs, frames, _, _ = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    img = synth.noise(H, W)
+    ts = []
+    t_end = time.perf_counter() + budget_s
+    while len(ts) < 2 or (time.perf_counter() < t_end and len(ts) < 20):
+        t0 = time.perf_counter()
+        O.conv_build(img, octs, S, threads=cores, want_dog=True)
+        ts.append(time.perf_counter() - t0)
+    med = float(np.median(ts))
+    return {"value": round(H * W / med / 1e6, 2), "unit": "Mpix/s", "cores": cores, "kind": "port",
+            "sample": f"own specification (no upstream convolution exists): orc_conv_build, double accumulation, OpenMP x{cores}, "
+                      f"one {W}x{H} frame x {octs} octaves, {len(ts)} reps, median", "ms_median": round(med * 1e3, 2)}
 
 
 def main():
     args = parse_args()
     out = run_reference(args) if args.impl == "reference" else run_native(args)
-    if (out and args.impl == "native" and args.mode == "ref" and not args.no_conv_extra and args.gpus == 1 and
-            dist_env()[1] == 1 and args.workload in ("c1", "c2", "c4")):
-        out["conv_mode"] = conv_extra(args)
     if out:
         print(json.dumps(out), flush=True)
 

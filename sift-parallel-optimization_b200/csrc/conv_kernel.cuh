@@ -74,7 +74,6 @@ struct ConvParams {
 };
 
 template <int R> __host__ __device__ constexpr int conv_ra() { return (R + 3) / 4 * 4; }          // aligned halo
-template <int R> __host__ __device__ constexpr int conv_th_max() { return R <= 6 ? 64 : 32; }   // tallest tile that keeps 2 CTAs/SM
 template <int R> __host__ __device__ constexpr int conv_pitch_in() {                            // 4 * odd
     int q = (CONV_TW + 2 * conv_ra<R>()) / 4;
     return 4 * (q | 1);
@@ -368,17 +367,10 @@ cudaError_t launch_conv_one(const ConvParams& P, cudaStream_t st, int device, in
     return cudaGetLastError();
 }
 
-// tall: 64-row tiles (less row-pass halo overhead) when the level has enough tiles to fill the GPU; otherwise
-// 32-row tiles: twice the CTAs, more of them resident, shorter per-CTA latency.
-// variant: bit 0 = 64-row tiles (radii <= 6 only), bit 1 = persistent double-buffered pipeline (float planes only)
+// (64-row tiles and persistent double-buffered CTAs were built and measured slower in round 1 and are gone; the
+//  NBUF template parameter of the kernel stays at 1.)
 template <int R, int SRC>
-cudaError_t launch_conv_th(const ConvParams& P, int variant, cudaStream_t st, int device, int frames, int sms) {
-    if constexpr (conv_th_max<R>() >= 64) {
-        if (variant & 1) return launch_conv_one<R, SRC, 64, 1>(P, st, device, frames, sms);
-    }
-    if constexpr (SRC == CONV_SRC_PLANE) {
-        if (variant & 2) return launch_conv_one<R, SRC, 32, 2>(P, st, device, frames, sms);
-    }
+cudaError_t launch_conv_th(const ConvParams& P, int /*variant*/, cudaStream_t st, int device, int frames, int sms) {
     return launch_conv_one<R, SRC, 32, 1>(P, st, device, frames, sms);
 }
 

@@ -182,7 +182,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;         // any bounded wait that gives up is reported by sspyr_sync
     std::memset(P.taps, 0, sizeof(P.taps));
     std::memcpy(P.taps + (RT - R), h->h_tables.data() + h->conv[level].taps_off, sizeof(float) * (2 * R + 1));
-    const int variant = (h->tune.conv_tall > 0 ? 1 : 0) | (h->tune.conv_pipe > 0 ? 2 : 0);   // default: 32-row, one tile per CTA
+    const int variant = 0;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     // The marching strip kernel (conv_march.cuh) row-filters every input row once and measured faster at every size;

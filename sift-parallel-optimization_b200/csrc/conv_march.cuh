@@ -26,13 +26,6 @@
 #pragma once
 #include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint)
 
-#ifndef SSPYR_STRIP_COLPASS
-#define SSPYR_STRIP_COLPASS 1            // column-pass mapping of the strip kernel: 1 = 4 columns x 4 rows per thread (default)
-#endif
-#ifndef SSPYR_STRIP_EPILOGUE
-#define SSPYR_STRIP_EPILOGUE 1           // 2 = evaluation build: running output pointers + an unchecked interior path
-#endif
-
 #include "conv_kernel.cuh"
 
 namespace sspyr {
@@ -136,10 +129,10 @@ __device__ __forceinline__ void strip_stage_rows(const ConvParams& P, float* __r
 }
 
 // Row pass of NROWS staged rows: sT[T0 + row][c] = sum_k taps[k] * sIn[row][RA + c + k - R]
-template <int R, int NROWS, int T0>
-__device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float* __restrict__ sIn, float* __restrict__ sT, int tid) {
+// (PIN = pitch of the staged rows; taps = 2R+1 values in the constant bank, centre at R)
+template <int R, int NROWS, int T0, int PIN = conv_pitch_in<R>()>
+__device__ __forceinline__ void strip_row_pass(const float* __restrict__ taps, const float* __restrict__ sIn, float* __restrict__ sT, int tid) {
     constexpr int RA = conv_ra<R>();
-    constexpr int PIN = conv_pitch_in<R>();
     constexpr int PT = conv_pitch_t();
     constexpr int NB = CONV_TW / CONV_PX;
     constexpr int NIN = CONV_PX + 2 * RA;
@@ -158,7 +151,7 @@ __device__ __forceinline__ void strip_row_pass(const ConvParams& P, const float*
         for (int i = 0; i < CONV_PX; ++i) acc[i] = 0.0f;
 #pragma unroll
         for (int k = 0; k <= 2 * R; ++k) {                     // taps outer: 16 independent FMA chains in flight
-            const float w = P.taps[k];                         // (packed FFMA2 here needs shifted operand pairs: the
+            const float w = taps[k];                           // (packed FFMA2 here needs shifted operand pairs: the
 #pragma unroll                                                 //  extra moves and registers made it slower, measured)
             for (int i = 0; i < CONV_PX; ++i) acc[i] = fmaf(w, in[i + k + (RA - R)], acc[i]);
         }
@@ -180,10 +173,10 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     constexpr int TH = STRIP_TH;
     constexpr int PIN = conv_pitch_in<R>();
     constexpr int PT = conv_pitch_t();
-    // Column-pass mapping: a thread owns PX adjacent columns x PY rows.  4 x 4 is the measured default; 2 x 8
-    // (SSPYR_STRIP_COLPASS=2, an evaluation build: make EXTRA=-DSSPYR_STRIP_COLPASS=2) reads 8+2R 64-bit words
-    // instead of 4+2R 128-bit ones per 16 outputs: 36 % fewer column-pass shared-memory wavefronts, same FMA count.
-    constexpr int PX = SSPYR_STRIP_COLPASS == 2 ? 2 : 4;
+    // Column-pass mapping: a thread owns PX = 4 adjacent columns x PY = 4 rows.  (A 2 x 8 mapping -- 36 % fewer
+    // column-pass shared-memory wavefronts -- and a running-pointer epilogue -- ~30 fewer instructions per step --
+    // were built and measured in round 2: both neutral to slower, profiles/r2_conv_eval_builds_ab.txt, and deleted.)
+    constexpr int PX = 4;
     constexpr int PY = 16 / PX;
     constexpr int TPB = CONV_TW / PX;                    // threads per row block of the column pass (32 or 64)
     static_assert(TPB * (TH / PY) == CONV_THREADS, "column-pass mapping must cover the step");
@@ -316,7 +309,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         phase ^= 1;
     }
     lost = __syncthreads_or(lost);                       // (CTA-uniform: threads time out individually)
-    if (!lost) strip_row_pass<R, 2 * R, 0>(P, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
+    if (!lost) strip_row_pass<R, 2 * R, 0>(P.taps, scratch, sT, tid);      // scratch (sT rows >= 2R) -> sT rows [0, 2R)
 
     const int cq = tid % TPB, rb = tid / TPB;           // column group / row block of the column pass
     const int x = x0 + cq * PX;
@@ -325,11 +318,6 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     float* d = P.dst_d ? P.dst_d + fz * P.dst_frame_stride : nullptr;
     float* dec = P.dst_dec ? P.dst_dec + fz * P.dst_frame_stride : nullptr;
 
-    // (evaluation build SSPYR_STRIP_EPILOGUE=2) running pointers to this thread's first output row of the step: the
-    // shipped epilogue rebuilds its 64-bit addresses from block / thread indices every step (~17 instructions) and
-    // every row (~6); these advance by one add per step and per row.
-    [[maybe_unused]] float* gq = g + (size_t)(y_begin + rb * PY) * P.dst_pitch + x;
-    [[maybe_unused]] float* dq = d ? d + (size_t)(y_begin + rb * PY) * P.dst_pitch + x : nullptr;
 #pragma unroll 1
     for (int k = 0; k < nsteps && !lost; ++k) {
         bool miss = false;
@@ -342,7 +330,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             }
         }
         if (__syncthreads_or(miss)) { lost = true; break; }   // new rows landed; carried rows are in place; scratch is free
-        strip_row_pass<R, TH, 2 * R>(P, sIn, sT, tid);
+        strip_row_pass<R, TH, 2 * R>(P.taps, sIn, sT, tid);
 
         // ---- centre values for DoG_{s-1} = G_{s-1} - G_s: input rows yr .. yr+PY-1 of this thread's quad ----
         // Output row y0 + m is staged row m - R of this step, so all but the first R rows of the step are still in
@@ -427,35 +415,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             unpk2(a01[j], acc[j][0], acc[j][1]);
             if constexpr (PX == 4) unpk2(a23[j], acc[j][2], acc[j][3]);
         }
-        if (SSPYR_STRIP_EPILOGUE == 2 && nvalid >= PX && yr + PY <= y_end) {      // interior: no per-row checks
-            float* gp = gq;
-            float* dp = dq;
-#pragma unroll
-            for (int j = 0; j < PY; ++j) {
-                if constexpr (PX == 4) {
-                    *reinterpret_cast<float4*>(gp) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-                    if (d) __stcs(reinterpret_cast<float4*>(dp), make_float4(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1],
-                                                                            cen[j][2] - acc[j][2], cen[j][3] - acc[j][3]));
-                } else {
-                    *reinterpret_cast<float2*>(gp) = make_float2(acc[j][0], acc[j][1]);
-                    if (d) __stcs(reinterpret_cast<float2*>(dp), make_float2(cen[j][0] - acc[j][0], cen[j][1] - acc[j][1]));
-                }
-                gp += P.dst_pitch;
-                if (d) dp += P.dst_pitch;
-                if (dec && (j & 1) == 0) {               // yr is even (segments and row blocks are): even j = even row
-                    const int dy = (yr + j) >> 1, dx = x >> 1;
-                    if (dy < P.dec_H && dx < P.dec_W) {
-                        float* q = dec + (size_t)dy * P.dec_pitch + dx;
-                        if constexpr (PX == 4) {
-                            if (dx + 1 < P.dec_W) *reinterpret_cast<float2*>(q) = make_float2(acc[j][0], acc[j][2]);
-                            else q[0] = acc[j][0];
-                        } else {
-                            q[0] = acc[j][0];
-                        }
-                    }
-                }
-            }
-        } else if (nvalid >= PX) {                       // full group: vector stores, one running offset
+        if (nvalid >= PX) {                              // full group: vector stores, one running offset
             unsigned o = (unsigned)yr * (unsigned)P.dst_pitch + (unsigned)x;   // a plane has < 2^32 floats
 #pragma unroll
             for (int j = 0; j < PY; ++j, o += (unsigned)P.dst_pitch) {
@@ -507,10 +467,6 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
                     }
                 }
             }
-        }
-        if (SSPYR_STRIP_EPILOGUE == 2) {
-            gq += (size_t)TH * P.dst_pitch;
-            if (d) dq += (size_t)TH * P.dst_pitch;
         }
         // carry the last 2R row-pass rows to the top: rows [TH, TH+2R) -> [0, 2R)   (disjoint since 2R <= TH).
         // Only the first CW row blocks' column passes read the destination rows (rb*PY < 2R), so only their warps meet

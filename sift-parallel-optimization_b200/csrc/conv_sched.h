@@ -42,6 +42,18 @@ inline bool level_chained(int conv_chain, long long ctas, int sms) {
     return conv_chain > 1 || (conv_chain == 1 && ctas > (long long)STRIP_CTAS_PER_SM * sms);
 }
 
+// Cascade (conv_cascade.cuh): segment height of an octave.  Consumers trail producers by about two diagonals of the
+// block order = 2 x levels x strips items, so the rows in flight between a plane's write and its read-back grow with
+// the segment height: keep that window (Gaussian planes only, DoG stores are streaming) near a third of the 126 MB
+// L2 -- 8192 / strips rows, a multiple of 32 in [32, 256].  The 2R warm-up rows of a segment are the price of short
+// segments (8K: 128 rows, +4 % row-pass work; 16K: 64 rows).
+inline int cascade_seg_rows(int W, int tuned) {
+    if (tuned > 0) return (tuned + STRIP_TH - 1) / STRIP_TH * STRIP_TH;
+    const int strips = (W + CONV_TW - 1) / CONV_TW;
+    int r = 8192 / (strips > 0 ? strips : 1) / STRIP_TH * STRIP_TH;
+    return r < STRIP_TH ? STRIP_TH : (r > 8 * STRIP_TH ? 8 * STRIP_TH : r);
+}
+
 // Frame lanes: builds of different frame slots in flight at once.  Row bands reading their neighbours' planes in
 // place keep at most 3: the CTAs at a band edge spin until the neighbour GPU has published the level they read, so
 // the builds in flight must stay few enough that waiting CTAs can never fill a GPU.

@@ -415,6 +415,7 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
     if (h->d_seg) cudaFree(h->d_seg);
     conv_drop_graphs(h);
+    conv_cascade_free(h);
     destroy_lanes(h);
     for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
@@ -520,8 +521,12 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
             if (!h->ext_in[f0])
                 while (done + n < count && f0 + n < h->cfg.frames && !h->ext_in[f0 + n]) ++n;
             cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            const bool capturing = cudaStreamIsCapturing(h->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone;
             const int nlanes = lane_count(h);
-            if (nlanes > 1 && cudaStreamIsCapturing(h->stream, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+            if (!capturing && conv_cascade_ok(h)) {          // one launch per build on the handle's stream (build numbers are
+                if (n > 64) n = 64;                          // launch parameters, so not while the caller captures a graph)
+                e = launch_conv_cascade(h, f0, n, &launches);
+            } else if (nlanes > 1 && !capturing)
                 e = build_on_lane(h, f0, n, nlanes, &launches);
             else
                 e = launch_conv_graphed(h, f0, n, &launches, own_streams(h));
@@ -894,9 +899,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "occ")) h->tune.occ = value;
     else if (!std::strcmp(key, "prefetch_next")) h->tune.prefetch_next = value;
     else if (!std::strcmp(key, "timing")) h->tune.timing = value;
-    else if (!std::strcmp(key, "conv_tall")) h->tune.conv_tall = value;
     else if (!std::strcmp(key, "conv_streams")) h->tune.conv_streams = value;
-    else if (!std::strcmp(key, "conv_pipe")) h->tune.conv_pipe = value;
     else if (!std::strcmp(key, "conv_march")) h->tune.conv_march = value;
     else if (!std::strcmp(key, "conv_graph")) h->tune.conv_graph = value;
     else if (!std::strcmp(key, "conv_tma")) h->tune.conv_tma = value;
@@ -904,6 +907,8 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_waves")) h->tune.conv_waves = value;
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
+    else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
+    else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;
     else if (!std::strcmp(key, "conv_l2hint")) h->tune.conv_l2hint = value;
     else if (!std::strcmp(key, "conv_lanes")) h->tune.conv_lanes = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);

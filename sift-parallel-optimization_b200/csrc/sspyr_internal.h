@@ -14,6 +14,8 @@
 
 namespace sspyr {
 
+struct CascMaps;                          // conv_cascade.cuh: per-octave tensor maps of the cascade kernel
+
 constexpr int CONV_FLAG_BLOCK = 64;       // CONV peer counters per frame slot: slot f uses d_flag[64 f ..): [0..15] per-octave
                                           // progress, [32..47] finished-CTA counts ([16] of slot 0: wait-timeout marker)
 
@@ -57,8 +59,6 @@ struct Tuning {
                                // handle has several slots and a frame is small next to the 126 MB L2 (measured: +10 % on
                                // 1080p, +4 % on 4K, -4 % on 8K where the frame itself would flush L2)
     int pdl = -1;              // programmatic dependent launch between consecutive builds; -1 = default (on)
-    int conv_tall = 0;         // CONV: 64-row tiles (radii <= 6)
-    int conv_pipe = 0;         // CONV: persistent double-buffered CTAs
     int conv_march = 1;        // CONV: marching strip kernel for radii <= 12 (0 = one-tile-per-CTA kernel everywhere)
     int conv_tma = 1;          // CONV strip kernel: TMA (cp.async.bulk.tensor) staging of interior steps
     int conv_waves = 0;        // CONV strip kernel: CTA waves to aim for (0 = automatic: 3, or 8-step segments, see march_seg_rows)
@@ -71,6 +71,9 @@ struct Tuning {
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int conv_lanes = 8;        // CONV: builds of different frame slots in flight at once (stream sets, <= 16), 1 = one at a
                                // time (measured, 1080p: 1 lane 0.163, 4 lanes 0.080 (5 slots) / 0.062, 8 lanes 0.056 ms per frame)
+    int conv_cascade = 1;      // CONV, whole frames: ONE launch per build, levels pipelined through L2 (conv_cascade.cuh);
+                               // 0 = one launch per level (conv_march.cuh), the only path for row bands
+    int conv_casc_seg = 0;     // cascade: segment height in rows (0 = automatic, cascade_seg_rows)
     int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
                                // as the segments of the previous level it reads are published (per-segment counters),
                                // instead of after the whole previous grid (0 = grid-wide dependency only)
@@ -130,6 +133,8 @@ struct sspyr_ctx {
     size_t seg_cap[SSPYR_MAX_OCTAVES] = {0};     // counters per level of that octave (strips x ceil(H/32))
     bool seg_dirty = false;                      // counters may be out of step (tuning changed, failed build): zero them first
     std::vector<unsigned> build_seq;             // per frame slot: builds started so far (all bands issue the same sequence)
+    sspyr::CascMaps* casc_maps = nullptr;        // cascade kernel: tensor maps (created on first use) and which octaves have one
+    bool casc_tma[SSPYR_MAX_OCTAVES] = {false};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     struct GraphEntry { int first, count, seen, launches; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;          // CONV: captured whole-pyramid launch sequences, by (first slot, count)
@@ -182,6 +187,9 @@ bool conv_has_down(const sspyr_ctx* h);
 float* conv_halo_plane(const sspyr_ctx* h, int octave, int down);
 unsigned char* conv_halo_raw(const sspyr_ctx* h, int down);
 cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches);
+bool conv_cascade_ok(const sspyr_ctx* h);
+cudaError_t launch_conv_cascade(sspyr_ctx* h, int first_frame, int count, int* launches);
+void conv_cascade_free(sspyr_ctx* h);
 
 inline const unsigned char* frame_input(const sspyr_ctx* h, int frame, size_t* pitch_bytes) {
     if (h->ext_in[frame]) {

@@ -20,7 +20,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
                 "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert key in d, key
     assert d["impl"] == "reference" and d["unit"] == "Mpix/s" and d["higher_is_better"] is True and d["vs_baseline"] is None
-    assert d["config"]["workload"].startswith("1920x1080") and "model" not in d["config"]
+    assert d["config"]["workload"].startswith("3840x2160") and "model" not in d["config"]      # default = c3, BASELINE's 1/2/4/8-GPU config
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -33,11 +33,15 @@ def test_other_ranks_of_the_reference_arm_exit_quietly():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
-def test_supplementary_conv_line_never_breaks_the_main_line():
-    """A default single-GPU run appends a CONV-mode figure measured by a child process; whatever happens to the
-    child (here: no GPU at all) the parent gets a small dict back, never an exception or a hang."""
-    import argparse
+def test_extras_tables_name_known_workloads():
+    """The extra records of a default run (other sharded workloads, CONV mode) are table-driven: every entry names a
+    BASELINE workload and a mode, and the N > 1 set contains the row-band CONV cases the north_star asks for."""
     sys.path.insert(0, ROOT)
     import bench
-    got = bench.conv_extra(argparse.Namespace(workload="c2"))
-    assert isinstance(got, dict) and ("unavailable" in got or "value" in got)
+    for key, wl, mode, steps, warm, e2e in bench.EXTRAS_N1:
+        assert wl in bench.WORKLOADS and mode in ("ref", "conv") and steps >= 1 and warm >= 3
+    keys = [k for k, *_ in bench.EXTRAS_NX]
+    assert {"c4_ref_rowband", "c4_conv_rowband", "c5_conv_rowband"} <= set(keys)
+    for key, wl, mode, steps, warm in bench.EXTRAS_NX:
+        assert bench.WORKLOADS[wl][4] in ("rowband", "batch") and warm >= 3
+    assert bench.WORKLOADS["c3"][3] == 256 and bench.parse_args.__module__ == "bench"

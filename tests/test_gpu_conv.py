@@ -79,7 +79,10 @@ def test_batched_frame_slots(pkg, O, synth):
         for f in range(n):
             ss.upload(frames[f], frame=f)
         ss.build_batch(0, n)
-        assert ss.last_launches() == 6 + 5 * (octs - 1)      # one launch per level for the whole batch
+        assert ss.last_launches() == 1                       # cascade: one launch for the whole batch, all levels
+        ss.set_tuning(conv_cascade=0)
+        ss.build_batch(0, n)
+        assert ss.last_launches() == 6 + 5 * (octs - 1)      # per-level path: one launch per level for the whole batch
         for f in (0, 3):
             check(ss.download_gauss(frame=f), O.conv_build(frames[f], octs, 3)["gauss"], 255.0, f"frame {f}")
 
@@ -157,7 +160,7 @@ def test_marching_kernel_equals_tile_kernel(pkg, O, synth, h, w, octs, S, rs):
     out = {}
     for march in (0, 1):
         with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=2) as ss:
-            ss.set_tuning(conv_march=march)
+            ss.set_tuning(conv_cascade=0, conv_march=march)
             ss.upload(img, frame=0)
             ss.upload(synth.noise(h, w, frame=5), frame=1)
             ss.build_batch(0, 2)
@@ -234,12 +237,15 @@ def _random_conv_geometries(seed, n):
 
 @pytest.mark.parametrize("h,w,octs,S,rs,march", _random_conv_geometries(77, 20) + [(1, 1, 1, 3, 3.0, 1), (2, 300, 2, 3, 3.0, 1),
                                                                                      (300, 2, 2, 3, 3.0, 0), (33, 129, 3, 3, 4.0, 1)])
-def test_random_geometries_conv_within_tolerance(pkg, O, synth, h, w, octs, S, rs, march):
-    """Seeded sweep of odd shapes for both CONV kernels (planes smaller than a tile, than the blur radius, ...)."""
+@pytest.mark.parametrize("cascade", [0, 1])
+def test_random_geometries_conv_within_tolerance(pkg, O, synth, h, w, octs, S, rs, march, cascade):
+    """Seeded sweep of odd shapes for all CONV kernels (planes smaller than a tile, than the blur radius, ...)."""
+    if cascade and not march:
+        pytest.skip("the cascade always marches")
     img = synth.noise(h, w, frame=h * 1000 + w)
     ref = O.conv_build(img, octs, S, radius_sigmas=rs)
     with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs) as ss:
-        ss.set_tuning(conv_march=march)
+        ss.set_tuning(conv_cascade=cascade, conv_march=march)
         ss.upload(img)
         ss.build()
         check(ss.download_gauss(), ref["gauss"], 255.0, "gauss")
@@ -261,7 +267,7 @@ def test_level_chaining_is_bit_identical(pkg, synth, h, w, octs, S, rs, frames):
     out = {}
     for chain in (0, 1, 2):
         with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=frames) as ss:
-            ss.set_tuning(conv_chain=chain)
+            ss.set_tuning(conv_cascade=0, conv_chain=chain)
             got = []
             for b in range(3):
                 for f in range(frames):
@@ -282,7 +288,7 @@ def test_level_chaining_survives_retuning_and_graph_replay(pkg, O, synth):
     a captured launch sequence (CUDA graph, from the 2nd build of a slot on) replays them correctly."""
     h, w, octs = 500, 900, 3
     with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=2) as ss:
-        ss.set_tuning(conv_chain=2)
+        ss.set_tuning(conv_cascade=0, conv_chain=2)
         for b in range(5):                                   # eager, capture, replays; alternating slots
             img = synth.noise(h, w, frame=b)
             ss.upload(img, frame=b % 2)
@@ -310,7 +316,7 @@ def test_frame_lanes_keep_stream_order(pkg, synth):
     def run(lanes):
         res = []
         with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n, outputs=pkg.OUT_ALL | pkg.OUT_EXTREMA) as ss:
-            ss.set_tuning(conv_lanes=lanes)
+            ss.set_tuning(conv_cascade=0, conv_lanes=lanes)
             for rnd in range(3):
                 for f in range(n):                       # upload -> build per slot, nothing waits in between
                     ss.upload(synth.noise(h, w, frame=100 * rnd + f), frame=f)
@@ -378,3 +384,113 @@ def test_peer_bands_with_several_builds_in_flight(pkg, synth, world, slots):
                         np.testing.assert_array_equal(got[octs + o], want[octs + o][:, row0 >> o:(row0 >> o) + (rows >> o)])
     for b in hs:
         b.close()
+
+
+# ---- the cascade: one launch per build, levels pipelined through L2 (conv_cascade.cuh) -----------------------------
+@pytest.mark.parametrize("h,w,octs,S,rs,frames,seg", [(270, 480, 4, 3, 3.0, 1, 0), (333, 1241, 3, 3, 3.0, 2, 32), (600, 700, 3, 2, 4.0, 1, 64),
+                                                      (97, 513, 2, 3, 3.0, 3, 0), (1080, 1920, 5, 3, 3.0, 2, 0), (2160, 3840, 5, 3, 3.0, 1, 0),
+                                                      (1500, 300, 6, 4, 3.0, 1, 96), (40, 3000, 3, 3, 3.0, 2, 0)])
+def test_cascade_equals_the_per_level_path_bit_for_bit(pkg, synth, h, w, octs, S, rs, frames, seg):
+    """The cascade is a schedule, not arithmetic: every plane of every frame equals the one-launch-per-level build,
+    build after build with new pixels every build (an item that ran ahead of its producer, or overwrote rows the
+    previous build was still reading, would show up as stale or torn rows), for several segment heights."""
+    imgs = [[synth.noise(h, w, frame=10 * b + f) for f in range(frames)] for b in range(3)]
+    out = {}
+    for cascade in (0, 1):
+        with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=frames) as ss:
+            ss.set_tuning(conv_cascade=cascade, conv_casc_seg=seg)
+            got = []
+            for b in range(3):
+                for f in range(frames):
+                    ss.upload(imgs[b][f], frame=f)
+                ss.build_batch(0, frames)
+                if cascade:
+                    assert ss.last_launches() == 1
+                ss.sync()
+                got.append([_all_planes(ss, f) for f in range(frames)])
+            out[cascade] = got
+    for b in range(3):
+        for f in range(frames):
+            for a, c in zip(out[0][b][f], out[1][b][f]):
+                np.testing.assert_array_equal(a, c)
+
+
+def test_cascade_builds_overlap_safely(pkg, O, synth):
+    """Back-to-back cascade launches with nothing in between overlap under programmatic dependent launch; the slot
+    epoch keeps two builds of the SAME slot apart and the item counters order everything else.  Many builds over a
+    ring of slots (and repeatedly over one slot) without a sync, then every slot must hold its last frame's pyramid."""
+    h, w, octs, n = 540, 960, 4, 3
+    frames = [synth.noise(h, w, frame=f) for f in range(n)]
+    want = [O.conv_build(fr, octs, 3) for fr in frames]
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n) as ss:
+        for f in range(n):
+            ss.upload(frames[f], frame=f)
+        for rnd in range(6):
+            for f in range(n):
+                ss.build(f)
+            ss.build(1)
+            ss.build(1)                                  # the same slot twice in a row
+        ss.sync()
+        for f in range(n):
+            check(ss.download_gauss(f), want[f]["gauss"], 255.0, f"slot {f} gauss")
+            check(ss.download_dog(f), want[f]["dog"], 255.0, f"slot {f} dog")
+        ss.set_tuning(conv_casc_seg=32)                  # retuning restarts the counters
+        ss.build_batch(0, n)
+        ss.build_batch(0, n)
+        ss.sync()
+        check(ss.download_gauss(2), want[2]["gauss"], 255.0, "after retuning")
+
+
+def test_cascade_pixel_types_and_device_input(pkg, O, synth):
+    import torch
+    h, w, octs = 300, 700, 4
+    img = synth.noise(h, w)
+    ref = O.conv_build(img, octs, 3)
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, pixel_type=pkg.PIXEL_U8) as ss:
+        ss.upload(img.astype(np.uint8))
+        ss.build()
+        assert ss.last_launches() == 1
+        check(ss.download_gauss(), ref["gauss"], 255.0, "u8")
+    t = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    st = torch.cuda.Stream()
+    with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, outputs=pkg.OUT_INPLACE) as ss:   # DoG + every Gaussian (CONV keeps them)
+        ss.set_stream(st.cuda_stream)
+        ss.set_input_device(t.data_ptr(), t.stride(0) * 4)
+        with torch.cuda.stream(st):
+            for rnd in range(3):                         # a producer kernel on the same stream right before each build
+                t.copy_(torch.from_numpy(synth.noise(h, w, frame=rnd)).cuda(), non_blocking=True)
+                t.add_(0)
+                ss.build()
+        ss.sync()
+        check(ss.download_gauss(), O.conv_build(synth.noise(h, w, frame=2), octs, 3)["gauss"], 255.0, "device input")
+
+
+# ---- independent fixture: the CUDA path against the committed scipy golden vectors (not only our own C oracle) --------
+@pytest.mark.parametrize("cascade", [1, 0])
+@pytest.mark.parametrize("name", ["noise_96x128", "noise_135x241", "noise_80x72_S2", "unit_64x96", "pattern_140x420"])
+def test_cuda_against_the_committed_scipy_fixture(pkg, name, cascade):
+    """tests/golden/conv_scipy.npz is generated by oracle/make_golden_conv.py from a statement of the CONV
+    specification that shares no code with the C oracle or the kernels (scipy.ndimage.correlate1d, double
+    accumulation).  Both CUDA schedules must meet the north_star's tolerance against it: 1e-4 of full scale per level."""
+    import importlib.util
+    import os
+    from conftest import GOLDEN, ROOT
+    gold = np.load(os.path.join(GOLDEN, "conv_scipy.npz"))
+    spec = importlib.util.spec_from_file_location("make_golden_conv", os.path.join(ROOT, "oracle", "make_golden_conv.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except ImportError:
+        pytest.skip("scipy not importable (only its CASES table and pixels() are used here)")
+    h, w, octs, S, s0, sin, rs, kind = mod.CASES[name]
+    img = mod.pixels(name, h, w, kind)
+    pix = pkg.PIXEL_F32 if kind == "f32" else pkg.PIXEL_I32
+    with pkg.ScaleSpace(h, w, octs, S, sigma0=s0, sigma_in=sin, radius_sigmas=rs, mode=pkg.MODE_CONV, pixel_type=pix) as ss:
+        ss.set_tuning(conv_cascade=cascade)
+        ss.upload(img)
+        ss.build()
+        gg, dd = ss.download_gauss(), ss.download_dog()
+    scale = 1.0 if kind == "f32" else 255.0
+    want = [gold[f"{name}_g{o}"] for o in range(octs)]
+    check(gg, want, scale, f"{name} gauss vs scipy")
+    check(dd, [g[:-1].astype(np.float64) - g[1:] for g in want], scale, f"{name} dog vs scipy")

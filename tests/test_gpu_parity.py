@@ -208,6 +208,32 @@ def test_device_resident_input_via_torch(pkg, O, synth):
             ss.set_input_device(t.data_ptr() + 4, 0)                         # misaligned
 
 
+def test_producer_kernel_right_before_the_build(pkg, O, synth):
+    """A build of a slot that reads a caller-produced device image is ordered after the producer's stores even though
+    consecutive library launches normally overlap (programmatic dependent launch): several rounds of
+    'producer kernel writes the image -> sspyr_build' on one stream with no sync in between."""
+    import torch
+    h, w = 1080, 1920
+    st = torch.cuda.Stream()
+    t = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+    with pkg.ScaleSpace(h, w, 5, 3, outputs=pkg.OUT_INPLACE, frames=2) as ss:
+        ss.set_stream(st.cuda_stream)
+        ss.upload(synth.noise(h, w, frame=99), frame=1)
+        ss.set_input_device(t.data_ptr(), t.stride(0) * 4, frame=0)
+        src = [torch.from_numpy(synth.noise(h, w, frame=k)).cuda() for k in range(4)]
+        torch.cuda.synchronize()
+        with torch.cuda.stream(st):
+            for k in range(4):
+                ss.build(1)                               # a PDL-launched neighbour in the stream
+                t.copy_(src[k])                           # producer kernel (device-to-device copy kernel + an elementwise op)
+                t.add_(1).sub_(1)
+                ss.build(0)
+        ss.sync()
+        ref = O.ref_build(synth.noise(h, w, frame=3), octaves=5, S=3, want=("inplace",))["inplace"]
+        for o, a in enumerate(ss.download_inplace(0)):
+            assert bits_equal(a, ref[o]), f"octave {o}"
+
+
 @pytest.mark.parametrize("rpt,block,bx,pdl,occ", [(1, 128, 0, 1, 0), (2, 256, 32, 1, 0), (4, 64, 64, 0, 1), (4, 256, 128, 1, 3),
                                                   (1, 256, 96, 0, 2), (2, 96, 96, 1, 5), (1, 32, 32, 1, 1)])
 def test_every_tuning_is_bit_exact(pkg, O, synth, rpt, block, bx, pdl, occ):

@@ -217,3 +217,38 @@ def test_conv_oracle_against_an_independent_scipy_restatement(O, h, w, octs, S, 
         np.testing.assert_allclose(got["gauss"][o], want, rtol=0, atol=2e-5 * 255)
         np.testing.assert_allclose(got["dog"][o], want[:-1] - want[1:], rtol=0, atol=4e-5 * 255)
         base = got["gauss"][o][S][::2, ::2][:h >> (o + 1), :w >> (o + 1)]      # (the oracle's own G_S: errors do not compound)
+
+
+# ---- CONV golden fixture (tests/golden/conv_scipy.npz, oracle/make_golden_conv.py): an independent scipy statement ----
+def _conv_golden_cases():
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_golden_conv", os.path.join(ROOT, "oracle", "make_golden_conv.py"))
+    try:
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)                       # needs scipy only to regenerate; CASES / pixels() do not
+    except ImportError:
+        return None
+    return mod
+
+
+@pytest.mark.parametrize("name", ["noise_96x128", "noise_135x241", "noise_80x72_S2", "unit_64x96", "pattern_140x420"])
+def test_conv_oracle_against_the_committed_scipy_fixture(O, name):
+    """orc_conv_build vs the committed golden vectors of the independent restatement: <= 2e-5 of full scale per
+    level (double accumulation on both sides; the fixture rounds the row pass to float like the kernels do)."""
+    import os
+    from conftest import GOLDEN
+    mod = _conv_golden_cases()
+    if mod is None:
+        pytest.skip("scipy not importable")
+    gold = np.load(os.path.join(GOLDEN, "conv_scipy.npz"))
+    h, w, octs, S, s0, sin, rs, kind = mod.CASES[name]
+    img = mod.pixels(name, h, w, kind)
+    got = O.conv_build(img, octs, S, sigma0=s0, sigma_in=sin, radius_sigmas=rs)
+    scale = 1.0 if kind == "f32" else 255.0
+    for o in range(octs):
+        want = gold[f"{name}_g{o}"]
+        assert got["gauss"][o].shape == want.shape
+        assert np.max(np.abs(got["gauss"][o].astype(np.float64) - want)) <= 2e-5 * scale, f"octave {o}"
+        assert np.max(np.abs(got["dog"][o].astype(np.float64) - (want[:-1].astype(np.float64) - want[1:]))) <= 4e-5 * scale
