@@ -1,6 +1,8 @@
 // csrc/conv_cascade.cu -- host side of the cascade build (conv_cascade.cuh): the parameter block of one launch, the
 // per-octave tensor maps, and the launch itself.  Its own translation unit: the kernel holds all twelve radii.
+#include <algorithm>
 #include <cstring>
+#include <vector>
 
 #include <cudaTypedefs.h>
 
@@ -46,6 +48,10 @@ bool make_octave_map(CUtensorMap* map, float* base, const OctGeom& g, int planes
 bool conv_cascade_ok(const sspyr_ctx* h) {
     if (h->cfg.mode != SSPYR_MODE_CONV || h->cfg.full_height != h->cfg.height || !h->d_seg || h->tune.conv_cascade == 0)
         return false;
+    // Automatic (conv_cascade = 1): frames of at least 4 Mpixel.  Below that every plane of a frame stays in L2 under the
+    // per-level schedule anyway, and the cascade's longer dependency chain per frame (levels trail one another by three
+    // steps, octaves follow one another) costs more than its single launch saves.  2 = always.
+    if (h->tune.conv_cascade == 1 && (long long)h->cfg.height * h->cfg.width < (4ll << 20)) return false;
     for (int s = 0; s < h->nl; ++s)
         if (h->conv[s].radius > CASC_MAX_R) return false;
     return true;
@@ -69,6 +75,8 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
         if (me == cudaSuccess) me = cudaMemset(h->d_flag, 0, sizeof(unsigned) * (size_t)CONV_FLAG_BLOCK * h->cfg.frames);
         if (me != cudaSuccess) return me;
         std::fill(h->build_seq.begin(), h->build_seq.end(), 0u);
+        if (h->d_casc_tab) cudaFree(h->d_casc_tab);
+        h->d_casc_tab = nullptr;
         h->seg_dirty = false;
     }
     CascParams C;
@@ -87,7 +95,9 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
     C.nl = h->nl;
     C.S = h->cfg.S;
     C.want_dog = (h->cfg.outputs & SSPYR_OUT_DOG) ? 1 : 0;
-    unsigned long long items = 0, real = 0;
+    CascItemGeom geom[SSPYR_MAX_OCTAVES];
+    int radius[SSPYR_MAX_LEVELS];
+    for (int s = 0; s < h->nl; ++s) radius[s] = cascade_radius_class(h->conv[s].radius);
     for (int o = 0; o < h->octaves; ++o) {
         const OctGeom& g = h->oct[o];
         CascOct& O = C.oct[o];
@@ -99,20 +109,28 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
         O.nsegs = (g.H + O.seg_rows - 1) / O.seg_rows;
         O.nstrips = (g.W + CONV_TW - 1) / CONV_TW;
         O.first_level = o == 0 ? 0 : 1;
-        O.item_base = (unsigned)items;
         O.seg_cap = (unsigned)h->seg_cap[o];
         O.tma = o < CASC_MAX_TMA_OCT && h->casc_tma[o];
-        const int nlev = h->nl - O.first_level;
-        items += (unsigned long long)(O.nsegs + 2 * (nlev - 1)) * nlev * O.nstrips;
-        real += (unsigned long long)O.nsegs * nlev * O.nstrips;
+        geom[o] = CascItemGeom{O.seg_rows, O.nsegs, O.nstrips, O.first_level, g.H, g.W};
+        if (O.nstrips > 1023 || O.nsegs > 16383) return cudaErrorInvalidValue;
     }
+    if (!h->d_casc_tab) {                                  // (dropped whenever the segmentation may change: seg_dirty)
+        bool keyed = false;
+        const std::vector<unsigned> tab = cascade_item_table(geom, h->octaves, h->nl, h->cfg.S, radius, &keyed);
+        cudaError_t me = cudaMalloc((void**)&h->d_casc_tab, sizeof(unsigned) * tab.size());
+        if (me == cudaSuccess) me = cudaMemcpy(h->d_casc_tab, tab.data(), sizeof(unsigned) * tab.size(), cudaMemcpyHostToDevice);
+        if (me != cudaSuccess) return me;
+        h->casc_items = (unsigned)tab.size();
+        h->casc_keyed = keyed;
+    }
+    const unsigned long long items = h->casc_items;
     if (items * (unsigned long long)count >= 0x7fffffffULL) return cudaErrorInvalidValue;
+    C.item_tab = h->d_casc_tab;
     C.items_per_frame = (unsigned)items;
-    C.real_items = (unsigned)real;
     for (int s = 0; s < h->nl; ++s) {
-        const int R = h->conv[s].radius;
-        C.lev[s].radius = R;
-        std::memcpy(C.lev[s].taps, h->h_tables.data() + h->conv[s].taps_off, sizeof(float) * (2 * R + 1));
+        const int R = h->conv[s].radius, RC = radius[s];
+        C.lev[s].radius = RC;                              // taps zero-padded to the class radius (bit-identical chains)
+        std::memcpy(C.lev[s].taps + (RC - R), h->h_tables.data() + h->conv[s].taps_off, sizeof(float) * (2 * R + 1));
     }
     for (int f = 0; f < count; ++f) C.bseq[f] = (unsigned short)(h->build_seq[first + f]++ & 0xffffu);
 
@@ -127,7 +145,7 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
     // only guaranteed visible at the kernel boundary) or raw device pointers are in the caller's hands.
     const bool pdl = h->tune.pdl != 0 && !h->ext_in[first] && !h->strict_order;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(items * count));
+    cfg.gridDim = dim3((unsigned)(items * (unsigned long long)count));
     cfg.blockDim = dim3(CONV_THREADS);
     cfg.dynamicSmemBytes = casc_smem_bytes();
     cfg.stream = h->stream;
@@ -144,6 +162,8 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
 void conv_cascade_free(sspyr_ctx* h) {
     delete h->casc_maps;
     h->casc_maps = nullptr;
+    if (h->d_casc_tab) cudaFree(h->d_casc_tab);
+    h->d_casc_tab = nullptr;
 }
 
 }  // namespace sspyr

@@ -10,10 +10,12 @@
 //
 //   * work item = the marching strip of conv_march.cuh: a 128-column strip, one vertical segment, one level; same
 //     arithmetic, same order -> bit-identical planes (tests compare the two paths bitwise);
-//   * block order = frame, octave, diagonal t = segment + 2 * level, level, strip.  Everything an item reads is
-//     produced by items with a SMALLER block index (level s-1, segments j-1..j+1: diagonals t-3..t-1; the octave
-//     above for the decimated base), and CTAs are dispatched in block-index order, so a waiting CTA's producers are
-//     always resident or finished: no deadlock, whatever fits on the GPU;
+//   * block order = frame, then a host-built item table (conv_cascade.cu): items sorted by the image row at which
+//     they can run -- segment + 2 per level inside an octave, the octaves interleaved so that octave o+1 follows level
+//     S of octave o down the frame instead of waiting for it to finish.  Everything an item reads is produced by items
+//     EARLIER in the table (the host verifies this for every item and falls back to the plain octave-major order
+//     otherwise), and CTAs are dispatched in block-index order, so a waiting CTA's producers are always resident or
+//     finished: no deadlock, whatever fits on the GPU;
 //   * ordering is carried by one 32-bit counter per item, (build << 16) | steps finished, published after every
 //     32-row step (st.release.gpu) and acquired by the consumer's first warp before it stages the rows
 //     (ld.acquire.gpu + fence.proxy.async, then one TMA box).  A consumer therefore trails its producer by two steps,
@@ -23,7 +25,9 @@
 //     touch.  No CUDA graph, no side streams, no events: one launch per build.
 //
 // Taps are read from the kernel parameter block through a level index that is only known at run time (uniform loads
-// into uniform registers); radii 1..12 are compiled into the one kernel and selected per item.
+// into uniform registers).  Radii are padded to three classes (6, 10, 12; zero taps at both ends leave every FMA chain
+// bit-identical): CTAs of different levels share an SM, and five different fully unrolled hot loops (10-14 KB each)
+// thrash its instruction cache (ncu: 23 % of all stall samples were no_instruction with one body per radius).
 #pragma once
 #include "conv_march.cuh"
 
@@ -43,7 +47,6 @@ struct CascOct {
     int H, W, pitch;
     int seg_rows, nsegs, nstrips;
     int first_level;                          // 0 for octave 0 (blurs the raw frame), 1 below (level 0 is the decimated base)
-    unsigned item_base;                       // first block index of this octave inside a frame
     unsigned seg_cap;                         // counters per level
     int tma;                                  // a tensor map for this octave exists (index = octave)
 };
@@ -61,8 +64,8 @@ struct CascParams {
     unsigned* slot_flags;                     // d_flag block of slot 0 of the launch (CONV_FLAG_BLOCK apart)
     unsigned* timeout_mark;
     unsigned ctr_frame_stride;
-    unsigned items_per_frame;                 // grid blocks per frame (with the empty corners of the diagonals)
-    unsigned real_items;                      // items that do work, per frame
+    const unsigned* item_tab;                 // block index inside a frame -> octave << 28 | level << 24 | strip << 14 | segment
+    unsigned items_per_frame;                 // work items (= grid blocks) per frame
     int raw_pitch, raw_kind;
     int slot0;                                // absolute index of the launch's first slot (TMA frame coordinate)
     int octaves, nl, S, want_dog;
@@ -426,7 +429,7 @@ __device__ __forceinline__ void cascade_item(const CascParams& C, const CascMaps
         if (lost) *C.timeout_mark = 0xC0000000u | (unsigned)strip;
         __threadfence();
         st_release(own, b16 + 0x10000u);
-        if (atomicAdd(flags + CASC_SLOT_FIN, 1u) == C.real_items - 1) {     // last item of this build of the slot
+        if (atomicAdd(flags + CASC_SLOT_FIN, 1u) == C.items_per_frame - 1) {     // last item of this build of the slot
             flags[CASC_SLOT_FIN] = 0;
             __threadfence();
             st_release(flags + CASC_SLOT_EPOCH, ((b16 >> 16) + 1u) & 0xffffu);
@@ -440,25 +443,13 @@ conv_cascade_kernel(const __grid_constant__ CascParams C, const __grid_constant_
     extern __shared__ __align__(128) float casc_smem[];
     asm volatile("griddepcontrol.launch_dependents;");    // the next build may fill SMs as this one drains (ordered by counters)
     const unsigned fz = blockIdx.x / C.items_per_frame;
-    unsigned it = blockIdx.x - fz * C.items_per_frame;
-    int o = 0;
-    while (o + 1 < C.octaves && it >= C.oct[o + 1].item_base) ++o;
-    const CascOct& O = C.oct[o];
-    it -= O.item_base;
-    const int nlev = C.nl - O.first_level;
-    const int strip = (int)(it % (unsigned)O.nstrips);
-    it /= (unsigned)O.nstrips;
-    const int sl = (int)(it % (unsigned)nlev);
-    const int seg = (int)(it / (unsigned)nlev) - 2 * sl;   // diagonal t = seg + 2 * sl
-    if (seg >= 0 && seg < O.nsegs) {
-        const int s = O.first_level + sl;
-        switch (C.lev[s].radius) {
-#define SSPYR_CASE(n) case n: cascade_item<n>(C, M, o, s, seg, strip, fz, casc_smem); break;
-            SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6)
-            SSPYR_CASE(7) SSPYR_CASE(8) SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
-#undef SSPYR_CASE
-            default: break;
-        }
+    const unsigned it = __ldg(C.item_tab + (blockIdx.x - fz * C.items_per_frame));
+    const int o = (int)(it >> 28), s = (int)((it >> 24) & 15u), strip = (int)((it >> 14) & 1023u), seg = (int)(it & 16383u);
+    switch (C.lev[s].radius) {                            // (the padded class radius)
+        case 6: cascade_item<6>(C, M, o, s, seg, strip, fz, casc_smem); break;
+        case 10: cascade_item<10>(C, M, o, s, seg, strip, fz, casc_smem); break;
+        case 12: cascade_item<12>(C, M, o, s, seg, strip, fz, casc_smem); break;
+        default: break;
     }
     // chain completion: "this grid done" implies "the grid it overlapped with done" for whatever follows in the stream
     asm volatile("griddepcontrol.wait;" ::: "memory");

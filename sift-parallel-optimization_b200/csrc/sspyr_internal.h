@@ -71,8 +71,9 @@ struct Tuning {
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int conv_lanes = 8;        // CONV: builds of different frame slots in flight at once (stream sets, <= 16), 1 = one at a
                                // time (measured, 1080p: 1 lane 0.163, 4 lanes 0.080 (5 slots) / 0.062, 8 lanes 0.056 ms per frame)
-    int conv_cascade = 1;      // CONV, whole frames: ONE launch per build, levels pipelined through L2 (conv_cascade.cuh);
-                               // 0 = one launch per level (conv_march.cuh), the only path for row bands
+    int conv_cascade = 1;      // CONV, whole frames: ONE launch per build, levels pipelined through L2 (conv_cascade.cuh):
+                               // 1 = for frames of >= 4 Mpixel, 2 = always, 0 = never (one launch per level, conv_march.cuh,
+                               // which is also the only path for row bands)
     int conv_casc_seg = 0;     // cascade: segment height in rows (0 = automatic, cascade_seg_rows)
     int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
                                // as the segments of the previous level it reads are published (per-segment counters),
@@ -135,6 +136,9 @@ struct sspyr_ctx {
     std::vector<unsigned> build_seq;             // per frame slot: builds started so far (all bands issue the same sequence)
     sspyr::CascMaps* casc_maps = nullptr;        // cascade kernel: tensor maps (created on first use) and which octaves have one
     bool casc_tma[SSPYR_MAX_OCTAVES] = {false};
+    unsigned* d_casc_tab = nullptr;              // cascade kernel: block index -> work item (rebuilt when the segmentation changes)
+    unsigned casc_items = 0;
+    bool casc_keyed = false;                     // the row-keyed order passed its dependency check (else: octave-major)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     struct GraphEntry { int first, count, seen, launches; cudaGraphExec_t exec; };
     std::vector<GraphEntry> graphs;          // CONV: captured whole-pyramid launch sequences, by (first slot, count)

@@ -78,6 +78,7 @@ def test_batched_frame_slots(pkg, O, synth):
     with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n) as ss:
         for f in range(n):
             ss.upload(frames[f], frame=f)
+        ss.set_tuning(conv_cascade=2)
         ss.build_batch(0, n)
         assert ss.last_launches() == 1                       # cascade: one launch for the whole batch, all levels
         ss.set_tuning(conv_cascade=0)
@@ -245,7 +246,7 @@ def test_random_geometries_conv_within_tolerance(pkg, O, synth, h, w, octs, S, r
     img = synth.noise(h, w, frame=h * 1000 + w)
     ref = O.conv_build(img, octs, S, radius_sigmas=rs)
     with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs) as ss:
-        ss.set_tuning(conv_cascade=cascade, conv_march=march)
+        ss.set_tuning(conv_cascade=2 * cascade, conv_march=march)
         ss.upload(img)
         ss.build()
         check(ss.download_gauss(), ref["gauss"], 255.0, "gauss")
@@ -398,14 +399,14 @@ def test_cascade_equals_the_per_level_path_bit_for_bit(pkg, synth, h, w, octs, S
     out = {}
     for cascade in (0, 1):
         with pkg.ScaleSpace(h, w, octs, S, mode=pkg.MODE_CONV, radius_sigmas=rs, frames=frames) as ss:
-            ss.set_tuning(conv_cascade=cascade, conv_casc_seg=seg)
+            ss.set_tuning(conv_cascade=2 * cascade, conv_casc_seg=seg)
             got = []
             for b in range(3):
                 for f in range(frames):
                     ss.upload(imgs[b][f], frame=f)
                 ss.build_batch(0, frames)
-                if cascade:
-                    assert ss.last_launches() == 1
+                if cascade and rs * 3.1 <= 12:                 # (radius_sigmas 4 gives radii up to 13: those handles stay on the
+                    assert ss.last_launches() == 1             #  per-level path, which must of course agree with itself)
                 ss.sync()
                 got.append([_all_planes(ss, f) for f in range(frames)])
             out[cascade] = got
@@ -423,6 +424,7 @@ def test_cascade_builds_overlap_safely(pkg, O, synth):
     frames = [synth.noise(h, w, frame=f) for f in range(n)]
     want = [O.conv_build(fr, octs, 3) for fr in frames]
     with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, frames=n) as ss:
+        ss.set_tuning(conv_cascade=2)
         for f in range(n):
             ss.upload(frames[f], frame=f)
         for rnd in range(6):
@@ -447,6 +449,7 @@ def test_cascade_pixel_types_and_device_input(pkg, O, synth):
     img = synth.noise(h, w)
     ref = O.conv_build(img, octs, 3)
     with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, pixel_type=pkg.PIXEL_U8) as ss:
+        ss.set_tuning(conv_cascade=2)
         ss.upload(img.astype(np.uint8))
         ss.build()
         assert ss.last_launches() == 1
@@ -455,6 +458,7 @@ def test_cascade_pixel_types_and_device_input(pkg, O, synth):
     st = torch.cuda.Stream()
     with pkg.ScaleSpace(h, w, octs, 3, mode=pkg.MODE_CONV, outputs=pkg.OUT_INPLACE) as ss:   # DoG + every Gaussian (CONV keeps them)
         ss.set_stream(st.cuda_stream)
+        ss.set_tuning(conv_cascade=2)
         ss.set_input_device(t.data_ptr(), t.stride(0) * 4)
         with torch.cuda.stream(st):
             for rnd in range(3):                         # a producer kernel on the same stream right before each build
@@ -486,7 +490,7 @@ def test_cuda_against_the_committed_scipy_fixture(pkg, name, cascade):
     img = mod.pixels(name, h, w, kind)
     pix = pkg.PIXEL_F32 if kind == "f32" else pkg.PIXEL_I32
     with pkg.ScaleSpace(h, w, octs, S, sigma0=s0, sigma_in=sin, radius_sigmas=rs, mode=pkg.MODE_CONV, pixel_type=pix) as ss:
-        ss.set_tuning(conv_cascade=cascade)
+        ss.set_tuning(conv_cascade=2 * cascade)
         ss.upload(img)
         ss.build()
         gg, dd = ss.download_gauss(), ss.download_dog()

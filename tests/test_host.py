@@ -205,3 +205,71 @@ int main() {
                     str(src), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout
+
+
+def test_cascade_block_order_is_dependency_safe(tmp_path):
+    """csrc/conv_sched.h cascade_item_table: the block order of the one-launch CONV build.  Deadlock freedom rests on
+    every work item coming after everything it reads (CTAs are dispatched in block order and spin on their producers'
+    counters), so the order is checked here, on the CPU, for BASELINE.json's shapes and for random geometries: the
+    row-keyed order must pass the check on the BASELINE shapes (it is the fast one), and whatever the function returns
+    must pass it always, hold every item exactly once and keep the strips of a group together."""
+    src = tmp_path / "casc.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <set>
+#include "conv_sched.h"
+using namespace sspyr;
+#define CHECK(c) do { if (!(c)) { std::printf("FAILED line %d: %s\n", __LINE__, #c); return 1; } } while (0)
+static int run(int H, int W, int octaves, int S, const int* rad, int seg_tuned, bool must_be_keyed) {
+    const int nl = S + 3;
+    CascItemGeom g[16];
+    int radius[16];
+    for (int s = 0; s < nl; ++s) radius[s] = cascade_radius_class(rad[s]);
+    size_t want = 0;
+    for (int o = 0; o < octaves; ++o) {
+        const int h = H >> o, w = W >> o;
+        const int sr = cascade_seg_rows(w, seg_tuned);
+        g[o] = CascItemGeom{sr, (h + sr - 1) / sr, (w + CONV_TW - 1) / CONV_TW, o == 0 ? 0 : 1, h, w};
+        want += (size_t)g[o].nsegs * g[o].nstrips * (nl - g[o].first_level);
+    }
+    bool keyed = false;
+    const std::vector<unsigned> tab = cascade_item_table(g, octaves, nl, S, radius, &keyed);
+    CHECK(tab.size() == want);
+    CHECK(std::set<unsigned>(tab.begin(), tab.end()).size() == want);         // every item exactly once
+    CHECK(cascade_order_is_safe(tab, g, octaves, nl, S, radius));
+    if (must_be_keyed) CHECK(keyed);
+    std::vector<unsigned> bad = tab;                                          // the checker does catch a broken order
+    if (bad.size() > 1 && (bad.front() >> 24) != (bad.back() >> 24)) { std::swap(bad.front(), bad.back()); CHECK(!cascade_order_is_safe(bad, g, octaves, nl, S, radius)); }
+    return 0;
+}
+int main() {
+    const int def[6] = {5, 4, 5, 6, 8, 10};                                   // sigma0 1.6, S = 3, radius 3 sigma
+    CHECK(cascade_seg_rows(7680, 0) == 128 && cascade_seg_rows(16384, 0) == 64 && cascade_seg_rows(3840, 0) == 256);
+    CHECK(cascade_seg_rows(1920, 0) == 256 && cascade_seg_rows(100, 0) == 256 && cascade_seg_rows(7680, 70) == 96);
+    CHECK(cascade_radius_class(1) == 6 && cascade_radius_class(6) == 6 && cascade_radius_class(7) == 10 && cascade_radius_class(12) == 12);
+    if (run(1080, 1920, 5, 3, def, 0, true)) return 1;                        // C2
+    if (run(2160, 3840, 5, 3, def, 0, true)) return 1;                        // C3
+    if (run(4320, 7680, 5, 3, def, 0, true)) return 1;                        // C4
+    if (run(16384, 16384, 8, 3, def, 0, true)) return 1;                      // C5
+    if (run(512, 512, 4, 3, def, 0, true)) return 1;                          // C1
+    for (int seg : {32, 64, 96, 160, 256}) if (run(4320, 7680, 5, 3, def, seg, true)) return 1;
+    unsigned long long x = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&](int lo, int hi) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return lo + (int)(x % (unsigned long long)(hi - lo + 1)); };
+    for (int it = 0; it < 300; ++it) {
+        const int H = rnd(1, 3000), W = rnd(1, 3000), S = rnd(1, 5);
+        int octs = 1;
+        while ((std::min(H, W) >> octs) >= 1 && octs < 8) ++octs;
+        octs = rnd(1, octs);
+        int rad[16];
+        for (int s = 0; s < S + 3; ++s) rad[s] = rnd(1, 12);
+        if (run(H, W, octs, S, rad, 32 * rnd(0, 8), false)) { std::printf("geometry %d x %d, %d octaves, S=%d\n", H, W, octs, S); return 1; }
+    }
+    std::printf("ok\n");
+    return 0;
+}
+''')
+    exe = tmp_path / "casc"
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=gnu++14", "-Wall", "-Werror", "-I", os.path.join(ROOT, "sift-parallel-optimization_b200", "csrc"),
+                    str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout
