@@ -422,11 +422,18 @@ def run_native(args) -> dict:
 
     # ---- end to end through the C ABI with HOST buffers ----------------------------------------------
     e2e = None
+    out_kp = None
     banded_conv = args.mode == "conv" and part == "rowband" and world > 1     # (driven through PeerExchanger: no e2e leg)
     if not args.no_e2e and rows and not banded_conv:
         e2e = run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my_frames, local, rank,
                       px_per_step_all, mode)
         e2e["host"] = topo
+        if part != "rowband" or world == 1:       # (the extremum scan treats a band's seams as image borders: whole frames only)
+            try:
+                out_kp = {pix: run_e2e_keypoints(pkg, torch, dist, sampler, args, rows, width, octs, my_frames, local, rank,
+                                                 px_per_step_all, mode, pix) for pix in ("i32", "u8")}
+            except Exception as e:                # a supplementary figure never breaks the main line
+                out_kp = {"unavailable": repr(e)[:300]}
     out = {"metric": METRIC, "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": world,
            "steps": rec.pop("steps"), "warmup": rec.pop("warmup"), "ms_per_step": rec.pop("ms_per_step"),
            "higher_is_better": True, "scaling": rec.pop("scaling"), "vs_baseline": None, "dtype": "f32",
@@ -435,6 +442,8 @@ def run_native(args) -> dict:
     out.update(rec)
     if e2e:
         out["e2e"] = e2e
+        if out_kp is not None:
+            out["e2e_keypoints"] = out_kp
     if rank == 0 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args.workload, budget_s=12.0)
     dist.barrier()
@@ -642,6 +651,72 @@ def run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my
             "api": "sspyr_upload + sspyr_build + sspyr_download_inplace per frame, pinned host buffers, "
                    "2 handles / 2 streams ping-pong", "result": "reference in-place layout (S+2 DoG + top Gaussian)",
             "checksum": checksum}
+
+
+def run_e2e_keypoints(pkg, torch, dist, sampler, args, rows, width, octs, my_frames, local, rank, px_per_step_all, mode,
+                      pixel: str = "i32") -> dict:
+    """End to end when the caller wants KEYPOINTS, not planes (the next SIFT step; csrc/extrema.cu): per frame
+    upload(pinned pixels) -> build (DoG planes only stay on the device) -> DoG extremum scan + compaction ->
+    download_keypoints(pinned).  A 1080p pyramid is 66 MB of planes but kilobytes of keypoints, which takes the path off
+    the PCIe link that bounds `e2e`.  Four handles / streams round-robin; whole frames only."""
+    import numpy as np
+    steps = 1 if args.workload == "c3" else max(3, min(args.steps if args.steps is not None else 30, 30))
+    lanes, cap = 4, 4096
+    pix = pkg.PIXEL_U8 if pixel == "u8" else pkg.PIXEL_I32
+    hs, streams, h_in, h_rec, h_cnt = [], [], [], [], []
+    for i in range(lanes):
+        st = torch.cuda.Stream(device=local)
+        h = pkg.ScaleSpace(rows, width, octs, S, mode=mode, outputs=pkg.OUT_DOG | pkg.OUT_KEYPOINTS, frames=1, device=local,
+                           pixel_type=pix, extrema_thresh=0.5, max_keypoints=1 << 18)
+        h.set_stream(st.cuda_stream)
+        img = pkg.synth.noise(rows, width, frame=9000 + rank * 10 + i)
+        tin = torch.from_numpy(img.astype(np.uint8) if pixel == "u8" else img).pin_memory()
+        hs.append(h); streams.append(st); h_in.append(tin)
+        h_rec.append(torch.zeros((cap, 4), dtype=torch.int32).pin_memory())
+        h_cnt.append(torch.zeros(1, dtype=torch.int32).pin_memory())
+    elem = 1 if pixel == "u8" else 4
+    busy = [False] * lanes
+    found = [0]
+
+    def one(i):
+        k = i % lanes
+        if busy[k]:
+            hs[k].sync()                          # the result of this handle's previous frame is now on the host
+            found[0] += int(h_cnt[k][0])
+        hs[k].upload_ptr(h_in[k].data_ptr(), width * elem)
+        hs[k].build()
+        hs[k].download_keypoints_ptr(h_rec[k].data_ptr(), cap, h_cnt[k].data_ptr())
+        busy[k] = True
+
+    n_frames = my_frames * steps
+    for i in range(min(2 * lanes, n_frames)):
+        one(i)
+    for h in hs:
+        h.sync()
+    busy = [False] * lanes
+    found[0] = 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler.active(True)
+    t0 = time.perf_counter()
+    for i in range(n_frames):
+        one(i)
+    for k, h in enumerate(hs):
+        h.sync()
+        if busy[k]:
+            found[0] += int(h_cnt[k][0])
+    dt = time.perf_counter() - t0
+    sampler.active(False)
+    dist.barrier()
+    dt = dist.max(dt)
+    for h in hs:
+        h.close()
+    return {"value": round(px_per_step_all * steps / dt / 1e6, 1), "unit": "Mpix/s",
+            "h2d_bytes_per_step": int(rows * width * elem * my_frames), "d2h_bytes_per_step": int((cap * 16 + 4) * my_frames),
+            "steps": steps, "ms_per_step": round(dt / steps * 1e3, 4), "pixels": pixel,
+            "keypoints_per_frame": round(found[0] / max(n_frames, 1), 1),
+            "api": "sspyr_upload + sspyr_build (outputs DOG|KEYPOINTS) + sspyr_download_keypoints per frame, pinned host buffers, "
+                   "4 handles / 4 streams round-robin", "result": "compacted list of 26-neighbour DoG extrema (|DoG| > 0.5)"}
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -60,6 +60,7 @@ extern "C" {
 #define SSPYR_OUT_DOG 2       /* S+2 DoG levels */
 #define SSPYR_OUT_GAUSS_TOP 4 /* only G_{S+2}: with DOG this is exactly the reference's in-place result */
 #define SSPYR_OUT_EXTREMA 8   /* 26-neighbour DoG extremum flags (uint8, S planes per octave); beyond the reference */
+#define SSPYR_OUT_KEYPOINTS 16 /* the same extrema as a compacted list of sspyr_keypoint records per frame slot */
 #define SSPYR_OUT_INPLACE (SSPYR_OUT_DOG | SSPYR_OUT_GAUSS_TOP)
 #define SSPYR_OUT_ALL (SSPYR_OUT_GAUSS | SSPYR_OUT_DOG)
 
@@ -73,6 +74,7 @@ extern "C" {
 #define SSPYR_KIND_DOG 1
 #define SSPYR_KIND_INPLACE 2 /* slot s of the reference's in-place layout: s<=S+1 -> DoG_s, s==S+2 -> G_{S+2} */
 #define SSPYR_KIND_EXTREMA 3
+#define SSPYR_KIND_KEYPOINTS 4 /* sspyr_device_ptr only: the slot's keypoint buffer, [uint32 count, uint32 capacity, 0, 0][records] */
 
 /* stages of the reference's pipeline a build can stop after (sspyr_build_stage) */
 #define SSPYR_STAGE_INIT 0   /* K0 only: every level = decimated original, GuassDePyramid.h:76-86 */
@@ -83,6 +85,15 @@ extern "C" {
 #define SSPYR_MAX_LEVELS 16 /* S + 3 <= 16 */
 
 typedef struct sspyr_ctx* sspyr_handle;
+
+/* One DoG extremum (SSPYR_OUT_KEYPOINTS): a pixel of DoG level `level` (1..S) of octave `octave` that is strictly greater
+ * or strictly smaller than its 26 neighbours in (level-1, level, level+1) and exceeds extrema_thresh in magnitude.
+ * x = column, y = row in that octave's coordinates (of the full image; row bands are not supported).  16 bytes. */
+typedef struct sspyr_keypoint {
+    int32_t x, y;
+    int32_t octave_level;  /* octave << 16 | level */
+    float value;           /* the DoG value */
+} sspyr_keypoint;
 
 /* Replaces the reference's compile-time constants and constructor arguments:
  *   sigma (GuassDePyramid.h:7), ctor (int** img, int len, int S) (:36), layer = floor(log2 len)+1 (:48-53). */
@@ -101,8 +112,9 @@ typedef struct sspyr_config {
     int32_t full_height;   /* rows of the full image; 0 = height */
     float sigma_in;        /* CONV: blur assumed present in the input (default 0.5) */
     float radius_sigmas;   /* CONV: tap radius = ceil(radius_sigmas * sigma_inc) (default 3.0) */
-    float extrema_thresh;  /* SSPYR_OUT_EXTREMA: |DoG| must exceed this */
-    int32_t reserved[8];   /* must be zero */
+    float extrema_thresh;  /* SSPYR_OUT_EXTREMA / _KEYPOINTS: |DoG| must exceed this */
+    int32_t max_keypoints; /* SSPYR_OUT_KEYPOINTS: records kept per frame slot (0 = 1 << 20); extrema beyond it are counted, not stored */
+    int32_t reserved[7];   /* must be zero */
 } sspyr_config;
 
 /* ---- life cycle ---------------------------------------------------------------------------------- */
@@ -166,6 +178,12 @@ SSPYR_API int sspyr_download(sspyr_handle h, int frame, int octave, int level, i
 SSPYR_API int sspyr_download_inplace(sspyr_handle h, int frame, float* dst);
 /* Same for all Gaussian levels: S+3 planes per octave. */
 SSPYR_API int sspyr_download_gauss(sspyr_handle h, int frame, float* dst);
+/* The keypoint list of a frame slot (SSPYR_OUT_KEYPOINTS; whole frames only -- a row band would treat its seams as image
+ * borders, so SSPYR_OUT_EXTREMA / _KEYPOINTS are rejected on band handles).  Enqueues two copies on the handle's stream:
+ * the number of extrema found -> *count, and the first min(capacity, max_keypoints) records -> dst, in no particular order.
+ * Both are asynchronous when the destinations are pinned (sspyr_host_alloc); call sspyr_sync() before reading.  *count may
+ * exceed what was stored: the list then holds the first max_keypoints extrema that reached the cursor. */
+SSPYR_API int sspyr_download_keypoints(sspyr_handle h, int frame, sspyr_keypoint* dst, int capacity, int* count);
 /* Device pointer of a plane (valid until sspyr_destroy).  From the first call on, CONV builds are ordered after
  * everything already enqueued on the handle's stream (the caller's kernels may now read the planes). */
 SSPYR_API int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind, void** ptr);

@@ -15,8 +15,8 @@ except Exception as e:
     print(sys.argv[2], 'FAILED', e)
 PY
 }
-for wl in ${WLS:-c4 c2 c3 c5}; do
+for wl in ${WLS:-c4 c3 c5 c2}; do
   run old_$wl --workload $wl --tune conv_cascade=0
-  run casc_$wl --workload $wl
-  for seg in ${SEGS:-}; do run casc_${wl}_seg$seg --workload $wl --tune conv_casc_seg=$seg; done
+  run casc_$wl --workload $wl --tune conv_cascade=2
+  for seg in ${SEGS:-}; do run casc_${wl}_seg$seg --workload $wl --tune conv_cascade=2,conv_casc_seg=$seg; done
 done 2>&1 | tee $O/results.txt

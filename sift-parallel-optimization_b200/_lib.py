@@ -15,11 +15,11 @@ LIB_PATH = os.path.join(_HERE, "libsspyr.so")
 # ---- constants (include/sspyr.h) -------------------------------------------------------------------
 OK, ERR_ARG, ERR_CUDA, ERR_NOMEM, ERR_STATE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 MODE_REF, MODE_CONV = 0, 1
-OUT_GAUSS, OUT_DOG, OUT_GAUSS_TOP, OUT_EXTREMA = 1, 2, 4, 8
+OUT_GAUSS, OUT_DOG, OUT_GAUSS_TOP, OUT_EXTREMA, OUT_KEYPOINTS = 1, 2, 4, 8, 16
 OUT_INPLACE = OUT_DOG | OUT_GAUSS_TOP
 OUT_ALL = OUT_GAUSS | OUT_DOG
 PIXEL_I32, PIXEL_F32, PIXEL_U8 = 0, 1, 2
-KIND_GAUSS, KIND_DOG, KIND_INPLACE, KIND_EXTREMA = 0, 1, 2, 3
+KIND_GAUSS, KIND_DOG, KIND_INPLACE, KIND_EXTREMA, KIND_KEYPOINTS = 0, 1, 2, 3, 4
 STAGE_INIT, STAGE_FILTER, STAGE_DOG = 0, 1, 2
 MAX_OCTAVES, MAX_LEVELS = 16, 16
 
@@ -29,7 +29,7 @@ SYMBOLS = (
     "sspyr_num_octaves", "sspyr_num_levels", "sspyr_num_dogs", "sspyr_level_dims", "sspyr_algorithmic_bytes",
     "sspyr_set_stream", "sspyr_upload", "sspyr_set_input_device", "sspyr_build", "sspyr_build_stage",
     "sspyr_build_batch", "sspyr_sync", "sspyr_elapsed_ms", "sspyr_last_launches", "sspyr_download",
-    "sspyr_download_inplace", "sspyr_download_gauss", "sspyr_device_ptr", "sspyr_window_table",
+    "sspyr_download_inplace", "sspyr_download_gauss", "sspyr_download_keypoints", "sspyr_device_ptr", "sspyr_window_table",
     "sspyr_host_alloc", "sspyr_host_free", "sspyr_conv_taps", "sspyr_set_tuning", "sspyr_halo_rows", "sspyr_halo_ptrs", "sspyr_conv_step",
     "sspyr_ipc_export", "sspyr_ipc_attach", "sspyr_peer_attach_local",
 )
@@ -44,7 +44,7 @@ class Config(C.Structure):
         ("sigma0", C.c_float), ("mode", C.c_int32), ("outputs", C.c_int32), ("pixel_type", C.c_int32),
         ("frames", C.c_int32), ("device", C.c_int32), ("band_row0", C.c_int32), ("full_height", C.c_int32),
         ("sigma_in", C.c_float), ("radius_sigmas", C.c_float), ("extrema_thresh", C.c_float),
-        ("reserved", C.c_int32 * 8),
+        ("max_keypoints", C.c_int32), ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
         "sspyr_download": ([H, i, i, i, i, vp, sz], i),
         "sspyr_download_inplace": ([H, i, vp], i),
         "sspyr_download_gauss": ([H, i, vp], i),
+        "sspyr_download_keypoints": ([H, i, vp, i, vp], i),
         "sspyr_device_ptr": ([H, i, i, i, i, C.POINTER(vp)], i),
         "sspyr_host_alloc": ([sz, C.POINTER(vp)], i),
         "sspyr_host_free": ([vp], i),

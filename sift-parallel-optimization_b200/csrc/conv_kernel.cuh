@@ -314,36 +314,6 @@ conv_level_kernel(const __grid_constant__ ConvParams P, int tiles_x, int tiles_y
     }
 }
 
-// 26-neighbour DoG extremum flags for one octave: flags[s-1][r][c] (s = 1..S), interior pixels only.
-__global__ void __launch_bounds__(256)
-extrema_kernel(const float* __restrict__ dog, unsigned char* __restrict__ flags, int S, int H, int W, int pitch,
-               unsigned long long plane, float thresh) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = blockIdx.y * blockDim.y + threadIdx.y;
-    const int s = blockIdx.z + 1;
-    if (c >= W || r >= H) return;
-    unsigned char f = 0;
-    if (r >= 1 && r < H - 1 && c >= 1 && c < W - 1) {
-        const float v = dog[(size_t)s * plane + (size_t)r * pitch + c];
-        if (fabsf(v) > thresh) {
-            bool is_max = true, is_min = true;
-#pragma unroll
-            for (int ds = -1; ds <= 1; ++ds)
-#pragma unroll
-                for (int dr = -1; dr <= 1; ++dr)
-#pragma unroll
-                    for (int dc = -1; dc <= 1; ++dc) {
-                        if (ds == 0 && dr == 0 && dc == 0) continue;
-                        const float n = __ldg(dog + (size_t)(s + ds) * plane + (size_t)(r + dr) * pitch + (c + dc));
-                        is_max &= v > n;
-                        is_min &= v < n;
-                    }
-            f = (is_max || is_min) ? 1 : 0;
-        }
-    }
-    flags[(size_t)(s - 1) * plane + (size_t)r * pitch + c] = f;
-}
-
 template <int R, int SRC, int TH, int NBUF>
 cudaError_t launch_conv_one(const ConvParams& P, cudaStream_t st, int device, int frames, int max_ctas) {
     constexpr size_t smem = conv_smem_bytes<R, TH, NBUF>();

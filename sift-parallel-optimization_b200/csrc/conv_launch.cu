@@ -19,7 +19,6 @@ SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
 #undef SSPYR_DECL
-cudaError_t launch_extrema_octave(const float*, unsigned char*, int, int, int, int, unsigned long long, float, cudaStream_t);
 
 namespace {
 
@@ -358,20 +357,6 @@ cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launche
     ge->launches = n;
     *launches += n;
     return cudaGraphLaunch(ge->exec, cs.main);
-}
-
-cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches) {
-    if (h->cfg.S < 1) return cudaSuccess;
-    for (int o = 0; o < h->octaves; ++o) {
-        const OctGeom& g = h->oct[o];
-        const float* dog = frame_out(h, frame) + g.off + (size_t)(h->nl - 1) * g.plane;
-        unsigned char* flags = h->d_ext + (size_t)frame * h->ext_frame_bytes + g.ext_off;
-        const cudaError_t e = launch_extrema_octave(dog, flags, h->cfg.S, g.H, g.W, g.pitch, g.plane,
-                                                    h->cfg.extrema_thresh, h->stream);
-        if (e != cudaSuccess) return e;
-        ++*launches;
-    }
-    return cudaSuccess;
 }
 
 }  // namespace sspyr

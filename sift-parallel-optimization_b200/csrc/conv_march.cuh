@@ -78,6 +78,15 @@ __device__ __forceinline__ void tma_load_3d_evict_first(void* smem_dst, const CU
 template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
     return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t()) + 16;   // + mbarrier
 }
+// Resident CTAs per SM the strip kernel is compiled for: 5 (48 registers, a few spilled words) where five tiles fit the
+// 228 KB of shared memory (radii <= 8), else 4 (64 registers).  The kernel is latency-bound at 32 warps per SM (issue slots
+// ~50 %, L1TEX ~70 %, DRAM ~55 %: round-2 cascade experiments, profiles/r2_conv_cascade.md), so more warps is what pays.
+#ifndef SSPYR_STRIP_OCC5
+#define SSPYR_STRIP_OCC5 1
+#endif
+template <int R> __host__ __device__ constexpr int strip_occupancy() {
+    return (SSPYR_STRIP_OCC5 && (strip_smem_bytes<R>() + 1024) * 5 <= 228 * 1024) ? 5 : 4;
+}
 
 namespace {
 
@@ -167,7 +176,7 @@ __device__ __forceinline__ void strip_row_pass(const float* __restrict__ taps, c
 // Steps that touch the frame edge (clamp-to-edge is not a TMA fill mode) or a neighbour band's halo rows keep
 // the cp.async path.
 template <int R, int SRC, bool TMA>
-__global__ void __launch_bounds__(CONV_THREADS, 4)
+__global__ void __launch_bounds__(CONV_THREADS, strip_occupancy<R>())
 conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __grid_constant__ CUtensorMap tmap) {
     static_assert(2 * R <= STRIP_TH, "the carried rows must fit above the new ones");
     constexpr int TH = STRIP_TH;
@@ -513,7 +522,7 @@ template <int R, int SRC, bool TMA>
 cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, const CUtensorMap& tmap,
                              int seg_rows, bool pdl) {
     constexpr size_t smem = strip_smem_bytes<R>();
-    static_assert(smem + 1024 <= (227 * 1024) / STRIP_CTAS_PER_SM, "the segmentation counts on 4 CTAs per SM");
+    static_assert(smem + 1024 <= (228 * 1024) / STRIP_CTAS_PER_SM, "the segmentation counts on at least 4 CTAs per SM");
     static bool configured[64] = {false};
     if (device < 0 || device >= 64 || !configured[device]) {
         cudaError_t e = cudaFuncSetAttribute(conv_strip_kernel<R, SRC, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,6 +1,7 @@
 // csrc/sspyr_api.cu -- the extern "C" boundary declared in include/sspyr.h: host state, window/tap
 // tables, buffer layout, copies.  All compute is in ref_kernels.cu / conv_kernels.cu; there is no CPU
 // implementation of the hot path anywhere in this library.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -185,6 +186,20 @@ cudaError_t build_on_lane(sspyr_ctx* h, int first, int count, int nlanes, int* l
     return cudaStreamWaitEvent(h->stream, L.done, 0);
 }
 
+// DoG extremum scan of slots first .. first+count-1 (modulo the slot count), one launch per contiguous run.
+cudaError_t scan_extrema(sspyr_ctx* h, int first, int count, int* launches) {
+    if (!(h->cfg.outputs & (SSPYR_OUT_EXTREMA | SSPYR_OUT_KEYPOINTS))) return cudaSuccess;
+    cudaError_t e = cudaSuccess;
+    int done = 0;
+    while (done < count && e == cudaSuccess) {
+        const int f0 = (first + done) % h->cfg.frames;
+        const int n = std::min(count - done, h->cfg.frames - f0);
+        e = launch_extrema(h, f0, n, launches);
+        done += n;
+    }
+    return e;
+}
+
 }  // namespace
 
 extern "C" {
@@ -234,9 +249,11 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
         if (cfg.band_row0 + cfg.height != cfg.full_height && cfg.height % align)
             return fail(nullptr, SSPYR_ERR_ARG, "interior band heights must be multiples of 2^(octaves-1)");
     }
-    if ((cfg.outputs & SSPYR_OUT_EXTREMA) && !(cfg.outputs & SSPYR_OUT_DOG))
-        return fail(nullptr, SSPYR_ERR_ARG, "SSPYR_OUT_EXTREMA needs SSPYR_OUT_DOG");
-    if ((cfg.outputs & SSPYR_OUT_EXTREMA) && banded)         // the scan treats the handle's first/last row as the image border
+    const int scan = cfg.outputs & (SSPYR_OUT_EXTREMA | SSPYR_OUT_KEYPOINTS);
+    if (scan && !(cfg.outputs & SSPYR_OUT_DOG))
+        return fail(nullptr, SSPYR_ERR_ARG, "SSPYR_OUT_EXTREMA / SSPYR_OUT_KEYPOINTS need SSPYR_OUT_DOG");
+    if (cfg.max_keypoints < 0) return fail(nullptr, SSPYR_ERR_ARG, "max_keypoints must be >= 0");
+    if (scan && banded)         // the scan treats the handle's first/last row as the image border
         return fail(nullptr, SSPYR_ERR_UNSUPPORTED, "SSPYR_OUT_EXTREMA is not available on a row-band handle (band seams would be "
                                                     "scanned as image borders); scan the bands' DoG planes with a whole-frame handle");
     if (cfg.mode == SSPYR_MODE_CONV) cfg.outputs |= SSPYR_OUT_GAUSS;   // the blur chain reads its own levels
@@ -377,6 +394,19 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
         }
     }
+    if (cfg.outputs & SSPYR_OUT_KEYPOINTS) {
+        h->kp_capacity = cfg.max_keypoints > 0 ? cfg.max_keypoints : (1 << 20);
+        h->kp_frame_bytes = round_up(16 + sizeof(sspyr_keypoint) * (size_t)h->kp_capacity, 256);
+        if ((e = dmalloc((void**)&h->d_kp, h->kp_frame_bytes * cfg.frames)) != cudaSuccess ||
+            (e = cudaMemset(h->d_kp, 0, h->kp_frame_bytes * cfg.frames)) != cudaSuccess) {
+            cudaGetLastError();
+            return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (keypoints): ") + cudaGetErrorString(e));
+        }
+        const unsigned cap = (unsigned)h->kp_capacity;       // header word 1 of every slot: the capacity
+        for (int f = 0; f < cfg.frames; ++f)
+            if ((e = cudaMemcpy(h->d_kp + (size_t)f * h->kp_frame_bytes + 4, &cap, 4, cudaMemcpyHostToDevice)) != cudaSuccess)
+                return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    }
     h->d_flag = reinterpret_cast<unsigned*>(h->d_out + h->frame_floats * cfg.frames);   // inside d_out: one IPC handle covers it
     h->build_seq.assign(cfg.frames, 0);
     if ((e = cudaMemset(h->d_flag, 0, (size_t)CONV_FLAG_BLOCK * cfg.frames * sizeof(float))) != cudaSuccess)
@@ -409,6 +439,7 @@ int sspyr_destroy(sspyr_handle h) {
     }
     if (h->d_out) cudaFree(h->d_out);
     if (h->d_ext) cudaFree(h->d_ext);
+    if (h->d_kp) cudaFree(h->d_kp);
     if (h->d_in) cudaFree(h->d_in);
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
@@ -505,8 +536,7 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
     cudaError_t e = cudaSuccess;
     if (h->cfg.mode == SSPYR_MODE_REF) {
         e = launch_ref(h, first, count, h->cfg.outputs, &launches);
-        for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
-            e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
+        if (e == cudaSuccess) e = scan_extrema(h, first, count, &launches);
     } else {
         const bool banded_conv = h->cfg.full_height != h->cfg.height;
         const bool peers_ok = (!conv_has_up(h) || h->peer[0].attached) && (!conv_has_down(h) || h->peer[1].attached);
@@ -532,9 +562,8 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
                 e = launch_conv_graphed(h, f0, n, &launches, own_streams(h));
             done += n;
         }
-        for (int i = 0; i < count && e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA); ++i)
-            e = launch_extrema(h, (first + i) % h->cfg.frames, &launches);
-        if (e == cudaSuccess && (h->cfg.outputs & SSPYR_OUT_EXTREMA)) e = mark_tail(h);
+        if (e == cudaSuccess) e = scan_extrema(h, first, count, &launches);
+        if (e == cudaSuccess && (h->cfg.outputs & (SSPYR_OUT_EXTREMA | SSPYR_OUT_KEYPOINTS))) e = mark_tail(h);
     }
     if (e != cudaSuccess) {
         h->seg_dirty = true;                                 // some levels may have counted this build, others not
@@ -599,6 +628,11 @@ int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind,
     if (!h || !ptr) return SSPYR_ERR_ARG;
     h->strict_order = true;       // the caller's own kernels may now touch the slots: builds follow the whole stream
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (kind == SSPYR_KIND_KEYPOINTS) {
+        if (!h->d_kp) return fail(h, SSPYR_ERR_STATE, "keypoint output not configured");
+        *ptr = h->d_kp + (size_t)frame * h->kp_frame_bytes;
+        return SSPYR_OK;
+    }
     if (kind == SSPYR_KIND_EXTREMA) {
         if (!h->d_ext) return fail(h, SSPYR_ERR_STATE, "extrema output not configured");
         if (octave < 0 || octave >= h->octaves || level < 0 || level >= h->cfg.S)
@@ -667,6 +701,20 @@ int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
         CU(h, copy_planes_to_host(dst, base + (size_t)(2 * nl - 2) * g.plane, g.W, g.pitch, g.H, h->stream));
         dst += (size_t)g.H * g.W;
     }
+    CU(h, mark_tail(h));
+    return SSPYR_OK;
+}
+
+int sspyr_download_keypoints(sspyr_handle h, int frame, sspyr_keypoint* dst, int capacity, int* count) {
+    if (!h || !count || capacity < 0 || (capacity > 0 && !dst)) return SSPYR_ERR_ARG;
+    if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
+    if (!h->d_kp) return fail(h, SSPYR_ERR_STATE, "keypoint output not configured (SSPYR_OUT_KEYPOINTS)");
+    if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
+    CU(h, cudaSetDevice(h->device));
+    const unsigned char* slot = h->d_kp + (size_t)frame * h->kp_frame_bytes;
+    CU(h, cudaMemcpyAsync(count, slot, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    const int n = capacity < h->kp_capacity ? capacity : h->kp_capacity;
+    if (n > 0) CU(h, cudaMemcpyAsync(dst, slot + 16, sizeof(sspyr_keypoint) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
     CU(h, mark_tail(h));
     return SSPYR_OK;
 }
@@ -775,8 +823,8 @@ int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
     if (e != cudaSuccess) return fail_cuda(h, e, "kernel launch");
     h->last_launches = launches;
     if (octave == h->octaves - 1 && level == h->nl - 1) {
-        if (h->cfg.outputs & SSPYR_OUT_EXTREMA) {
-            const cudaError_t e2 = launch_extrema(h, frame, &launches);
+        if (h->cfg.outputs & (SSPYR_OUT_EXTREMA | SSPYR_OUT_KEYPOINTS)) {
+            const cudaError_t e2 = launch_extrema(h, frame, 1, &launches);
             if (e2 != cudaSuccess) return fail_cuda(h, e2, "kernel launch");
         }
         h->built[frame] = 1;
@@ -909,6 +957,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
     else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
     else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;
+    else if (!std::strcmp(key, "conv_casc_debug")) h->tune.conv_casc_debug = value;
     else if (!std::strcmp(key, "conv_l2hint")) h->tune.conv_l2hint = value;
     else if (!std::strcmp(key, "conv_lanes")) h->tune.conv_lanes = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);

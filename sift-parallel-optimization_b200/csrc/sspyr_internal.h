@@ -71,10 +71,11 @@ struct Tuning {
     int conv_streams = 1;      // CONV: run octaves on concurrent streams
     int conv_lanes = 8;        // CONV: builds of different frame slots in flight at once (stream sets, <= 16), 1 = one at a
                                // time (measured, 1080p: 1 lane 0.163, 4 lanes 0.080 (5 slots) / 0.062, 8 lanes 0.056 ms per frame)
-    int conv_cascade = 1;      // CONV, whole frames: ONE launch per build, levels pipelined through L2 (conv_cascade.cuh):
+    int conv_cascade = 0;      // CONV, whole frames: ONE launch per build, levels pipelined through L2 (conv_cascade.cuh):
                                // 1 = for frames of >= 4 Mpixel, 2 = always, 0 = never (one launch per level, conv_march.cuh,
                                // which is also the only path for row bands)
     int conv_casc_seg = 0;     // cascade: segment height in rows (0 = automatic, cascade_seg_rows)
+    int conv_casc_debug = 0;   // cascade timing experiments (WRONG results): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
     int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
                                // as the segments of the previous level it reads are published (per-segment counters),
                                // instead of after the whole previous grid (0 = grid-wide dependency only)
@@ -101,6 +102,9 @@ struct sspyr_ctx {
     float* d_out = nullptr;                  // cfg.frames slots
     unsigned char* d_ext = nullptr;          // extrema flags (optional)
     size_t ext_frame_bytes = 0;
+    unsigned char* d_kp = nullptr;           // keypoint lists (optional): per slot [count, capacity, 0, 0][int4 records]
+    size_t kp_frame_bytes = 0;
+    int kp_capacity = 0;
     unsigned char* d_in = nullptr;           // cfg.frames input slots
     size_t in_pitch_bytes = 0, in_frame_bytes = 0, elem_bytes = 4;
     std::vector<const void*> ext_in;         // per-slot external device input (nullptr = own slot)
@@ -190,7 +194,7 @@ bool conv_has_up(const sspyr_ctx* h);
 bool conv_has_down(const sspyr_ctx* h);
 float* conv_halo_plane(const sspyr_ctx* h, int octave, int down);
 unsigned char* conv_halo_raw(const sspyr_ctx* h, int down);
-cudaError_t launch_extrema(const sspyr_ctx* h, int frame, int* launches);
+cudaError_t launch_extrema(const sspyr_ctx* h, int first_frame, int count, int* launches);
 bool conv_cascade_ok(const sspyr_ctx* h);
 cudaError_t launch_conv_cascade(sspyr_ctx* h, int first_frame, int count, int* launches);
 void conv_cascade_free(sspyr_ctx* h);

@@ -30,7 +30,7 @@ class ScaleSpace:
     def __init__(self, height: int, width: int, octaves: int = 0, S: int = 3, sigma0: float = 0.0,
                  mode: int = L.MODE_REF, outputs: int = L.OUT_ALL, pixel_type: int = L.PIXEL_I32,
                  frames: int = 1, device: int = -1, band_row0: int = 0, full_height: int = 0,
-                 sigma_in: float = 0.5, radius_sigmas: float = 3.0, extrema_thresh: float = 0.0):
+                 sigma_in: float = 0.5, radius_sigmas: float = 3.0, extrema_thresh: float = 0.0, max_keypoints: int = 0):
         self._lib = L.load()
         cfg = L.Config()
         L.check(None, self._lib.sspyr_default_config(C.byref(cfg)))
@@ -38,6 +38,7 @@ class ScaleSpace:
         cfg.sigma0, cfg.mode, cfg.outputs, cfg.pixel_type = sigma0, mode, outputs, pixel_type
         cfg.frames, cfg.device, cfg.band_row0, cfg.full_height = frames, device, band_row0, full_height
         cfg.sigma_in, cfg.radius_sigmas, cfg.extrema_thresh = sigma_in, radius_sigmas, extrema_thresh
+        cfg.max_keypoints = max_keypoints
         self._h = C.c_void_p()
         L.check(None, self._lib.sspyr_create(C.byref(cfg), C.byref(self._h)))
         self.height, self.width, self.S, self.frames = height, width, S, max(frames, 1)
@@ -161,6 +162,19 @@ class ScaleSpace:
     def download_dog(self, frame: int = 0) -> list[np.ndarray]:
         return [np.stack([self.download(o, s, L.KIND_DOG, frame) for s in range(self.dogs)])
                 for o in range(self.octaves)]
+
+    def download_keypoints(self, frame: int = 0, capacity: int = 1 << 20) -> tuple[np.ndarray, int]:
+        """(records [n, 4] int32: x, y, octave << 16 | level, value bits; number of extrema found).  Synchronises."""
+        rec = np.empty((capacity, 4), dtype=np.int32)
+        cnt = np.zeros(1, dtype=np.int32)
+        self._ck(self._lib.sspyr_download_keypoints(self._h, frame, C.c_void_p(rec.ctypes.data), capacity, C.c_void_p(cnt.ctypes.data)))
+        self.sync()
+        n = int(cnt[0])
+        return rec[:min(n, capacity)], n
+
+    def download_keypoints_ptr(self, rec_ptr: int, capacity: int, count_ptr: int, frame: int = 0) -> None:
+        """Async variant into caller-owned (pinned) memory; call sync() before reading."""
+        self._ck(self._lib.sspyr_download_keypoints(self._h, frame, C.c_void_p(rec_ptr), capacity, C.c_void_p(count_ptr)))
 
     def download_inplace_ptr(self, host_ptr: int, frame: int = 0) -> None:
         """Async variant into caller-owned (pinned) memory; call sync() before reading."""

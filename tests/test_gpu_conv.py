@@ -134,22 +134,55 @@ def test_bands_match_the_unbanded_gpu_result_exactly(pkg, synth):
         b.close()
 
 
-def test_extrema_flags(pkg, O, synth):
-    h, w, octs, S = 96, 128, 3, 3
-    img = synth.noise(h, w)
+@pytest.mark.parametrize("h,w,octs,S", [(96, 128, 3, 3), (135, 241, 3, 3), (270, 480, 4, 2), (64, 1030, 2, 4), (17, 70, 1, 3)])
+def test_extrema_flags_and_keypoints(pkg, O, synth, h, w, octs, S):
+    """The tiled DoG extremum scan (csrc/extrema.cu): flag planes equal the oracle's scan of the SAME DoG planes exactly,
+    and the compacted keypoint list holds exactly the flagged pixels -- position, octave, level and DoG value -- in
+    both modes; tiles that straddle the plane edge, planes smaller than a tile, several frame slots in one launch."""
+    thresh = 0.5
     for mode in (pkg.MODE_CONV, pkg.MODE_REF):
-        with pkg.ScaleSpace(h, w, octs, S, mode=mode, outputs=pkg.OUT_ALL | pkg.OUT_EXTREMA, extrema_thresh=0.5) as ss:
-            ss.upload(img)
-            ss.build()
-            dd = ss.download_dog()
-            total = 0
-            for o in range(octs):
-                want = O.extrema_octave(dd[o], 0.5)              # scan of the GPU's own DoG planes: exact
-                got = np.stack([ss.download(o, s, pkg.KIND_EXTREMA) for s in range(S)])
-                np.testing.assert_array_equal(got, want)
-                total += int(want.sum())
-            if mode == pkg.MODE_CONV:
-                assert total > 0
+        frames = 2
+        with pkg.ScaleSpace(h, w, octs, S, mode=mode, outputs=pkg.OUT_ALL | pkg.OUT_EXTREMA | pkg.OUT_KEYPOINTS,
+                            extrema_thresh=thresh, frames=frames) as ss:
+            for f in range(frames):
+                ss.upload(synth.noise(h, w, frame=f), frame=f)
+            ss.build_batch(0, frames)
+            for f in range(frames):
+                dd = ss.download_dog(frame=f)
+                rec, found = ss.download_keypoints(frame=f)
+                want_list = []
+                for o in range(octs):
+                    want = O.extrema_octave(dd[o], thresh)               # scan of the GPU's own DoG planes: exact
+                    got = np.stack([ss.download(o, s, pkg.KIND_EXTREMA, frame=f) for s in range(S)])
+                    np.testing.assert_array_equal(got, want)
+                    for s, y, x in np.argwhere(want):
+                        want_list.append((int(x), int(y), (o << 16) | (int(s) + 1), int(dd[o][s + 1][y, x].view(np.int32))))
+                assert found == len(want_list) == len(rec)
+                assert sorted(map(tuple, rec.tolist())) == sorted(want_list)
+                if mode == pkg.MODE_CONV and h * w > 5000:
+                    assert found > 0
+
+
+def test_keypoint_capacity_and_errors(pkg, synth):
+    h, w = 200, 300
+    with pkg.ScaleSpace(h, w, 3, 3, mode=pkg.MODE_CONV, outputs=pkg.OUT_DOG | pkg.OUT_KEYPOINTS, max_keypoints=50) as ss:
+        ss.upload(synth.noise(h, w))
+        ss.build()
+        rec, found = ss.download_keypoints(capacity=1000)
+        assert found > 50 and len(rec) == 50                         # counted beyond the capacity, stored up to it
+        assert ss.device_ptr(0, 0, pkg.KIND_KEYPOINTS) != 0
+        ss.build()                                                   # the cursor restarts with every build
+        assert ss.download_keypoints(capacity=10)[1] == found
+    with pytest.raises(pkg.SspyrError):                              # needs DoG
+        pkg.ScaleSpace(h, w, 3, 3, outputs=pkg.OUT_GAUSS | pkg.OUT_KEYPOINTS)
+    with pytest.raises(pkg.SspyrError) as e:                         # band seams would be scanned as image borders
+        pkg.ScaleSpace(64, w, 2, 3, outputs=pkg.OUT_ALL | pkg.OUT_KEYPOINTS, band_row0=0, full_height=128)
+    assert e.value.code == pkg._lib.ERR_UNSUPPORTED
+    with pkg.ScaleSpace(h, w, 3, 3) as ss:
+        ss.upload(synth.noise(h, w))
+        ss.build()
+        with pytest.raises(pkg.SspyrError):
+            ss.download_keypoints()                                  # not configured
 
 
 @pytest.mark.parametrize("h,w,octs,S,rs", [(270, 480, 4, 3, 3.0), (135, 1241, 3, 3, 3.0), (600, 700, 3, 3, 4.0),
