@@ -40,6 +40,7 @@ constexpr int CONV_THREADS = 256;
 
 // input kinds of a level kernel
 constexpr int CONV_FLAG_STRIDE = 32;      // progress-counter values per build (>= levels)
+constexpr int CONV_FLAG_EPOCH = 51;       // d_flag[64 slot + 51]: builds of the slot started (row bands over peer memory)
 constexpr int CONV_FLAG_TIMEOUT = 16;     // d_flag[0..15]: per-octave counters; d_flag[16]: wait-timeout marker (slot 0's block)
 constexpr int CONV_SRC_PLANE = 3;       // float plane of the previous level (SSPYR_PIXEL_* = 0,1,2 are raw frames)
 
@@ -58,9 +59,11 @@ struct ConvParams {
     // Peer-memory row bands, synchronisation fused into the strip kernel (null = not used):
     const unsigned* wait_up;            // neighbour-above's progress counter: CTAs that stage its rows wait for `wait_need`
     const unsigned* wait_dn;            // neighbour-below's
-    unsigned wait_need;
+    unsigned wait_need;                 // (relative to the build: the kernel adds (*epoch - 1) * CONV_FLAG_STRIDE)
     unsigned* signal_flag;              // this band's counter for this octave: the last CTA to finish publishes signal_value
-    unsigned signal_value;
+    unsigned signal_value;              // (relative, like wait_need)
+    const unsigned* epoch;              // builds of this frame slot started so far, bumped on the device at the start of a build:
+                                        // no launch parameter changes from build to build, so the sequence replays as a CUDA graph
     unsigned* done_count;               // CTAs finished so far (self-resetting)
     unsigned* timeout_mark;
     // Level chaining inside one octave (strip kernel, null = not used): every (strip, segment) CTA counts its builds

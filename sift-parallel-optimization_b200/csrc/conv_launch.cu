@@ -22,26 +22,52 @@ SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
 
 namespace {
 
-// One thread publishes "this band has finished `value` level steps" to its neighbours (system-scope release:
-// everything the preceding kernels in the stream wrote is visible to a peer GPU that acquires the counter).
-__global__ void conv_signal_kernel(unsigned* flag, unsigned value) {
+// One thread publishes "this band has finished level `value` of the running build" to its neighbours (system-scope
+// release: everything the preceding kernels in the stream wrote is visible to a peer GPU that acquires the counter).
+// Counter values are (build - 1) * CONV_FLAG_STRIDE + level + 1 with the build number read from the slot's epoch word.
+__global__ void conv_signal_kernel(unsigned* flag, unsigned value, const unsigned* epoch) {
     __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(value) : "memory");
+    const unsigned v = (*epoch - 1u) * CONV_FLAG_STRIDE + value;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(v) : "memory");
 }
 
-// One thread waits until the neighbour's counter reaches `need`.  The neighbour runs on another GPU, so it
-// makes progress on its own; a bounded spin (about 2 s) marks flag[1] instead of hanging the device.
-__global__ void conv_wait_kernel(const unsigned* peer_flag, int count, unsigned need, unsigned* my_flags) {
+// One thread waits until the neighbour's counter reaches `need` (relative to the running build).  The neighbour runs
+// on another GPU, so it makes progress on its own; a bounded spin (about 2 s) marks the handle instead of hanging.
+__global__ void conv_wait_kernel(const unsigned* peer_flag, unsigned need, const unsigned* epoch, unsigned* my_flags) {
+    const unsigned want = (*epoch - 1u) * CONV_FLAG_STRIDE + need;
     const long long t0 = clock64();
-    for (int i = 0; i < count; ++i) {            // `count` consecutive counters must all have reached `need`
-        for (;;) {
-            unsigned v;
-            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peer_flag + i) : "memory");
-            if (v >= need) break;
-            if (clock64() - t0 > 4000000000LL) { my_flags[CONV_FLAG_TIMEOUT] = need; return; }
-            __nanosleep(200);
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(peer_flag) : "memory");
+        if (v >= want) break;
+        if (clock64() - t0 > 4000000000LL) { my_flags[CONV_FLAG_TIMEOUT] = want; return; }
+        __nanosleep(200);
+    }
+}
+
+// First kernel of a banded build: next build number of the slot (on the DEVICE -- the launch sequence has no per-build
+// parameters and replays as a CUDA graph), then "nothing of this build may be written before both neighbours have
+// finished reading the previous one": every octave counter of theirs at its end-of-build value.
+__global__ void conv_begin_kernel(unsigned* epoch, const unsigned* peer_up, const unsigned* peer_dn, int octaves, int nl,
+                                  unsigned* my_flags) {
+    const unsigned b = *epoch + 1u;
+    if (b >= 2u) {
+        const unsigned prev_done = (b - 2u) * CONV_FLAG_STRIDE + (unsigned)nl;
+        const long long t0 = clock64();
+        for (int side = 0; side < 2; ++side) {
+            const unsigned* f = side == 0 ? peer_up : peer_dn;
+            if (!f) continue;
+            for (int o = 0; o < octaves; ++o)
+                for (;;) {
+                    unsigned v;
+                    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f + o) : "memory");
+                    if (v >= prev_done) break;
+                    if (clock64() - t0 > 4000000000LL) { my_flags[CONV_FLAG_TIMEOUT] = prev_done; o = octaves; break; }
+                    __nanosleep(200);
+                }
         }
     }
+    *epoch = b;
 }
 
 // compiled radius that serves a requested one (taps are zero-padded up to it)
@@ -222,10 +248,10 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     //  slots can be in flight at once)
     unsigned* my_flags = h->d_flag + (size_t)CONV_FLAG_BLOCK * first;
     const size_t peer_block = (size_t)CONV_FLAG_BLOCK * first;
-    const unsigned epoch = (h->build_seq[first] - 1) * CONV_FLAG_STRIDE;
+    const unsigned* epoch = my_flags + CONV_FLAG_EPOCH;      // bumped by conv_begin_kernel at the start of every build
     const bool first_level = octave == 0 && level == 0;
     const int wo = (level == 1 && octave > 0) ? octave - 1 : octave;
-    const unsigned need = epoch + (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;
+    const unsigned need = (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;   // relative to the build
     const bool fused_sync = peered && march && h->tune.conv_fused_sync != 0;
     if (fused_sync) {
         if (!first_level) {
@@ -234,13 +260,14 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
             P.wait_need = need;
         }
         P.signal_flag = my_flags + octave;
-        P.signal_value = epoch + (unsigned)level + 1;
+        P.signal_value = (unsigned)level + 1;
         P.done_count = my_flags + 32 + octave;
+        P.epoch = epoch;
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
     } else if (peered && !first_level) {
         for (int side = 0; side < 2; ++side)
             if (h->peer[side].attached) {
-                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + peer_block + wo, 1, need, h->d_flag);
+                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + peer_block + wo, need, epoch, h->d_flag);
                 ++*launches;
             }
     }
@@ -248,26 +275,22 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {
-        conv_signal_kernel<<<1, 1, 0, st>>>(my_flags + octave, epoch + (unsigned)level + 1);
+        conv_signal_kernel<<<1, 1, 0, st>>>(my_flags + octave, (unsigned)level + 1, epoch);
         ++*launches;
         e = cudaGetLastError();
     }
     return e;
 }
 
-// Start of a build on a band with attached neighbours: next epoch; nothing of this build may be written before
-// both neighbours have finished reading the previous one (every octave counter at its end-of-build value).
+// Start of a build on a band with attached neighbours: one single-thread kernel (conv_begin_kernel).
 cudaError_t conv_begin_build(sspyr_ctx* h, int slot, cudaStream_t st, int* launches) {
     if (!(h->peer[0].attached || h->peer[1].attached)) return cudaSuccess;
-    const unsigned b = ++h->build_seq[slot];
-    if (b >= 2) {
-        const unsigned prev_done = (b - 2) * CONV_FLAG_STRIDE + (unsigned)h->nl;
-        for (int side = 0; side < 2; ++side)
-            if (h->peer[side].attached) {
-                conv_wait_kernel<<<1, 1, 0, st>>>(h->peer[side].flag + (size_t)CONV_FLAG_BLOCK * slot, h->octaves, prev_done, h->d_flag);
-                ++*launches;
-            }
-    }
+    ++h->build_seq[slot];
+    unsigned* my_flags = h->d_flag + (size_t)CONV_FLAG_BLOCK * slot;
+    const size_t blk = (size_t)CONV_FLAG_BLOCK * slot;
+    conv_begin_kernel<<<1, 1, 0, st>>>(my_flags + CONV_FLAG_EPOCH, h->peer[0].attached ? h->peer[0].flag + blk : nullptr,
+                                       h->peer[1].attached ? h->peer[1].flag + blk : nullptr, h->octaves, h->nl, h->d_flag);
+    ++*launches;
     return cudaGetLastError();
 }
 
@@ -310,7 +333,6 @@ void conv_drop_graphs(sspyr_ctx* h) {
 // launch_conv, replayed as a CUDA graph from the second build of the same slots on: 26+ small launches and
 // their cross-stream events cost more host time than the small levels take on the GPU.
 cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launches, const ConvStreams& cs) {
-    const bool peered = h->peer[0].attached || h->peer[1].attached;
     if (h->seg_dirty && h->d_seg) {          // segment counters possibly out of step: restart all of them from zero
         conv_drop_graphs(h);                 // (rare: after sspyr_set_tuning or a failed build; every lane has been
         cudaError_t me = cudaStreamSynchronize(h->stream);   //  joined into the handle's stream, so this drains them all)
@@ -319,7 +341,11 @@ cudaError_t launch_conv_graphed(sspyr_ctx* h, int first, int count, int* launche
     }
     h->seg_dirty = false;
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (h->tune.conv_graph == 0 || peered || cudaStreamIsCapturing(cs.main, &st) != cudaSuccess ||
+    // (row bands over peer memory included: their build number lives on the device, conv_begin_kernel)
+    // Not when a neighbour band lives on the SAME GPU (single-GPU tests of the band protocol): kernels that wait on one
+    // another must be able to run side by side, and two graphs launched on one device are not guaranteed to.
+    const bool neighbour_here = (h->peer[0].attached && h->peer[0].same_device) || (h->peer[1].attached && h->peer[1].same_device);
+    if (h->tune.conv_graph == 0 || neighbour_here || cudaStreamIsCapturing(cs.main, &st) != cudaSuccess ||
         st != cudaStreamCaptureStatusNone)
         return launch_conv(h, first, count, launches, cs);
     sspyr_ctx::GraphEntry* ge = nullptr;

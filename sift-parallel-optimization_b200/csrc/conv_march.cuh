@@ -78,15 +78,8 @@ __device__ __forceinline__ void tma_load_3d_evict_first(void* smem_dst, const CU
 template <int R> __host__ __device__ constexpr size_t strip_smem_bytes() {
     return sizeof(float) * ((size_t)STRIP_TH * conv_pitch_in<R>() + (size_t)(STRIP_TH + 2 * R) * conv_pitch_t()) + 16;   // + mbarrier
 }
-// Resident CTAs per SM the strip kernel is compiled for: 5 (48 registers, a few spilled words) where five tiles fit the
-// 228 KB of shared memory (radii <= 8), else 4 (64 registers).  The kernel is latency-bound at 32 warps per SM (issue slots
-// ~50 %, L1TEX ~70 %, DRAM ~55 %: round-2 cascade experiments, profiles/r2_conv_cascade.md), so more warps is what pays.
-#ifndef SSPYR_STRIP_OCC5
-#define SSPYR_STRIP_OCC5 1
-#endif
-template <int R> __host__ __device__ constexpr int strip_occupancy() {
-    return (SSPYR_STRIP_OCC5 && (strip_smem_bytes<R>() + 1024) * 5 <= 228 * 1024) ? 5 : 4;
-}
+// (Compiling the kernel for 5 resident CTAs per SM -- 48 registers, a few spilled words, possible for radii <= 8 -- was
+//  measured 3-6 % SLOWER than 4 CTAs at 64 registers on every workload, profiles/r2_conv_experiments.md; it stays at 4.)
 
 namespace {
 
@@ -176,7 +169,7 @@ __device__ __forceinline__ void strip_row_pass(const float* __restrict__ taps, c
 // Steps that touch the frame edge (clamp-to-edge is not a TMA fill mode) or a neighbour band's halo rows keep
 // the cp.async path.
 template <int R, int SRC, bool TMA>
-__global__ void __launch_bounds__(CONV_THREADS, strip_occupancy<R>())
+__global__ void __launch_bounds__(CONV_THREADS, STRIP_CTAS_PER_SM)
 conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __grid_constant__ CUtensorMap tmap) {
     static_assert(2 * R <= STRIP_TH, "the carried rows must fit above the new ones");
     constexpr int TH = STRIP_TH;
@@ -261,7 +254,9 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     // Fused halo synchronisation (row bands over peer memory): only the CTAs whose rows reach into a neighbour
     // band wait for that neighbour to have published the level they read; interior CTAs start at once, so the
     // halo latency hides behind the band's interior.
+    const unsigned band_epoch = P.epoch ? (*P.epoch - 1u) * CONV_FLAG_STRIDE : 0u;   // (written by the build's first kernel)
     if (tid == 0) {
+        const unsigned wait_need = band_epoch + P.wait_need;
         const bool need_up = P.wait_up && y_begin - R < 0;
         const bool need_dn = P.wait_dn && y_begin + nsteps * TH + R > P.H;
         for (int side = 0; side < 2; ++side) {
@@ -271,8 +266,8 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             for (;;) {
                 unsigned v;
                 asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                if (v >= P.wait_need) break;
-                if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = P.wait_need; break; }
+                if (v >= wait_need) break;
+                if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = wait_need; break; }
                 __nanosleep(100);
             }
         }
@@ -512,7 +507,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
             if (atomicAdd(P.done_count, 1u) == total - 1) {
                 *P.done_count = 0;                       // ready for the next launch on this octave's stream
                 __threadfence_system();
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.signal_flag), "r"(P.signal_value) : "memory");
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.signal_flag), "r"(band_epoch + P.signal_value) : "memory");
             }
         }
     }

@@ -7,10 +7,23 @@
 #include <cstring>
 #include <new>
 
+#include <nvtx3/nvToolsExt.h>     // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
+
 #include "conv_sched.h"
 #include "sspyr_internal.h"
 
 using namespace sspyr;
+
+namespace {
+// NVTX range around one library call (tracing): upload / build / download show up by name on the
+// host timeline of Nsight Systems / Compute next to the kernels they enqueue.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
 
 namespace {
 
@@ -495,6 +508,7 @@ int sspyr_set_stream(sspyr_handle h, void* cuda_stream) {
 }
 
 int sspyr_upload(sspyr_handle h, int frame, const void* host, size_t pitch_bytes) {
+    NvtxRange nvtx_("sspyr_upload");
     if (!h || !host) return SSPYR_ERR_ARG;
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     const size_t row = (size_t)h->cfg.width * h->elem_bytes;
@@ -528,6 +542,7 @@ int sspyr_set_input_device(sspyr_handle h, int frame, const void* dev, size_t pi
 }
 
 int sspyr_build_batch(sspyr_handle h, int first, int count) {
+    NvtxRange nvtx_("sspyr_build");
     if (!h) return SSPYR_ERR_ARG;
     if (!valid_frame(h, first) || count < 1) return fail(h, SSPYR_ERR_ARG, "bad frame range");
     CU(h, cudaSetDevice(h->device));
@@ -579,6 +594,7 @@ int sspyr_build_batch(sspyr_handle h, int first, int count) {
 int sspyr_build(sspyr_handle h, int frame) { return sspyr_build_batch(h, frame, 1); }
 
 int sspyr_build_stage(sspyr_handle h, int frame, int stage) {
+    NvtxRange nvtx_("sspyr_build_stage");
     if (!h) return SSPYR_ERR_ARG;
     if (stage == SSPYR_STAGE_DOG) return sspyr_build_batch(h, frame, 1);
     if (stage != SSPYR_STAGE_INIT && stage != SSPYR_STAGE_FILTER) return fail(h, SSPYR_ERR_ARG, "bad stage");
@@ -599,6 +615,7 @@ int sspyr_build_stage(sspyr_handle h, int frame, int stage) {
 }
 
 int sspyr_sync(sspyr_handle h) {
+    NvtxRange nvtx_("sspyr_sync");
     if (!h) return SSPYR_ERR_ARG;
     CU(h, cudaSetDevice(h->device));
     CU(h, cudaStreamSynchronize(h->stream));
@@ -648,6 +665,7 @@ int sspyr_device_ptr(sspyr_handle h, int frame, int octave, int level, int kind,
 }
 
 int sspyr_download(sspyr_handle h, int frame, int octave, int level, int kind, void* dst, size_t pitch_bytes) {
+    NvtxRange nvtx_("sspyr_download");
     if (!h || !dst) return SSPYR_ERR_ARG;
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
@@ -668,6 +686,7 @@ int sspyr_download(sspyr_handle h, int frame, int octave, int level, int kind, v
 }
 
 int sspyr_download_inplace(sspyr_handle h, int frame, float* dst) {
+    NvtxRange nvtx_("sspyr_download_inplace");
     if (!h || !dst) return SSPYR_ERR_ARG;
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
@@ -687,6 +706,7 @@ int sspyr_download_inplace(sspyr_handle h, int frame, float* dst) {
 }
 
 int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
+    NvtxRange nvtx_("sspyr_download_gauss");
     if (!h || !dst) return SSPYR_ERR_ARG;
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (!h->built[frame]) return fail(h, SSPYR_ERR_STATE, "frame slot has not been built since its last upload");
@@ -706,6 +726,7 @@ int sspyr_download_gauss(sspyr_handle h, int frame, float* dst) {
 }
 
 int sspyr_download_keypoints(sspyr_handle h, int frame, sspyr_keypoint* dst, int capacity, int* count) {
+    NvtxRange nvtx_("sspyr_download_keypoints");
     if (!h || !count || capacity < 0 || (capacity > 0 && !dst)) return SSPYR_ERR_ARG;
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
     if (!h->d_kp) return fail(h, SSPYR_ERR_STATE, "keypoint output not configured (SSPYR_OUT_KEYPOINTS)");
@@ -809,6 +830,7 @@ int sspyr_halo_ptrs(sspyr_handle h, int frame, int octave, int level, void** sen
 }
 
 int sspyr_conv_step(sspyr_handle h, int frame, int octave, int level) {
+    NvtxRange nvtx_("sspyr_conv_step");
     if (!h) return SSPYR_ERR_ARG;
     if (h->cfg.mode != SSPYR_MODE_CONV) return fail(h, SSPYR_ERR_STATE, "sspyr_conv_step is for CONV mode");
     if (!valid_frame(h, frame)) return fail(h, SSPYR_ERR_ARG, "frame slot out of range");
@@ -925,6 +947,7 @@ int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
     q.in_frame_bytes = n->in_frame_bytes;
     for (int o = 0; o < h->octaves; ++o) { q.H[o] = n->oct[o].H; q.off[o] = n->oct[o].off; q.plane[o] = n->oct[o].plane; }
     q.local = true;
+    q.same_device = n->device == h->device;
     q.attached = true;
     return SSPYR_OK;
 }

@@ -121,6 +121,8 @@ struct sspyr_ctx {
     // being copied into d_halo; progress counters in peer memory order the steps (conv_launch.cu).
     struct Peer {
         bool attached = false, local = false;
+        bool same_device = false;                // neighbour band lives on THIS GPU (tests): its kernels must be able to run
+                                                 // beside ours, so the launch sequence is not replayed as a graph
         const float* out = nullptr;              // neighbour's d_out
         const unsigned char* in = nullptr;       // neighbour's d_in
         const unsigned* flag = nullptr;          // neighbour's progress counter

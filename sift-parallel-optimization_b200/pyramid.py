@@ -43,6 +43,7 @@ class ScaleSpace:
         L.check(None, self._lib.sspyr_create(C.byref(cfg), C.byref(self._h)))
         self.height, self.width, self.S, self.frames = height, width, S, max(frames, 1)
         self.mode, self.outputs, self.pixel_type = mode, outputs or L.OUT_ALL, pixel_type
+        self.max_keypoints = max_keypoints or (1 << 20)
         self.octaves = self._lib.sspyr_num_octaves(self._h)
         self.levels = self._lib.sspyr_num_levels(self._h)
         self.dogs = self._lib.sspyr_num_dogs(self._h)
@@ -170,7 +171,7 @@ class ScaleSpace:
         self._ck(self._lib.sspyr_download_keypoints(self._h, frame, C.c_void_p(rec.ctypes.data), capacity, C.c_void_p(cnt.ctypes.data)))
         self.sync()
         n = int(cnt[0])
-        return rec[:min(n, capacity)], n
+        return rec[:min(n, capacity, self.max_keypoints)], n
 
     def download_keypoints_ptr(self, rec_ptr: int, capacity: int, count_ptr: int, frame: int = 0) -> None:
         """Async variant into caller-owned (pinned) memory; call sync() before reading."""

@@ -165,11 +165,11 @@ def test_extrema_flags_and_keypoints(pkg, O, synth, h, w, octs, S):
 
 def test_keypoint_capacity_and_errors(pkg, synth):
     h, w = 200, 300
-    with pkg.ScaleSpace(h, w, 3, 3, mode=pkg.MODE_CONV, outputs=pkg.OUT_DOG | pkg.OUT_KEYPOINTS, max_keypoints=50) as ss:
+    with pkg.ScaleSpace(h, w, 3, 3, mode=pkg.MODE_CONV, outputs=pkg.OUT_DOG | pkg.OUT_KEYPOINTS, max_keypoints=5) as ss:
         ss.upload(synth.noise(h, w))
         ss.build()
         rec, found = ss.download_keypoints(capacity=1000)
-        assert found > 50 and len(rec) == 50                         # counted beyond the capacity, stored up to it
+        assert found > 5 and len(rec) == 5                           # counted beyond the capacity, stored up to it
         assert ss.device_ptr(0, 0, pkg.KIND_KEYPOINTS) != 0
         ss.build()                                                   # the cursor restarts with every build
         assert ss.download_keypoints(capacity=10)[1] == found
