@@ -73,6 +73,7 @@ def parse_args():
                     help="CONV row bands: read neighbour planes in the kernel over NVLink (CUDA IPC) or NCCL send/recv")
     ap.add_argument("--slots", type=int, default=0, help="frame slots in the ring (0 = enough to cover 4x L2, 2..8)")
     ap.add_argument("--tune", default="", help="rows_per_thread=2,block=256,bx=0,pdl=1")
+    ap.add_argument("--extras-tune", default="", help="tuning applied to the extra records only (A/B runs)")
     return ap.parse_args()
 
 
@@ -131,6 +132,15 @@ class Dist:
         t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
         return float(t.item())
+
+    def gather(self, v: float) -> list:
+        """One float per rank, in rank order, on every rank."""
+        if self.world == 1:
+            return [v]
+        t = self.torch.zeros(self.world, dtype=self.torch.float64, device=self.dev)
+        t[self.dist.get_rank()] = v
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.tolist()]
 
     def close(self):
         if self.world > 1:
@@ -304,6 +314,8 @@ def measure(pkg, torch, dist, sampler, wl: str, mode_name: str, outputs_name: st
             cursor[0] = (cursor[0] + n) % slots
             left -= n
 
+    if exchanger is not None and halo == "peer":
+        warmup = max(warmup, 3 * slots + 1)       # every slot's launch sequence is captured on its 2nd and replayed from its 3rd build
     for _ in range(warmup):
         step()
     torch.cuda.synchronize()
@@ -470,6 +482,9 @@ class Solo:
     def sum(self, v):
         return v
 
+    def gather(self, v):
+        return [v]
+
 
 EXTRAS_N1 = [  # (key, workload, mode, steps, warmup, e2e)
     ("c2_ref", "c2", "ref", 500, 20, True),
@@ -526,7 +541,7 @@ def run_extras(pkg, torch, dist, sampler, args, world, rank, local) -> dict:
         try:
             t0 = time.perf_counter()
             r = measure(pkg, torch, dist, sampler, wl, mode, "all", world, rank, local, steps, warm, halo=args.halo,
-                        per_step_pass=False)
+                        tune=args.extras_tune, per_step_pass=False)
             rec = slim(r)
             dist.barrier()
             n1 = None
@@ -641,6 +656,11 @@ def run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my
     ec.record(streams[0])
     hs[0].sync()
     h2d_ms, d2h_ms = ea.elapsed_time(eb), eb2.elapsed_time(ec)
+    # every rank's copy rates, measured at the same moment (all ranks copy at once after the barrier above): shows where
+    # the host side of the link saturates as N grows
+    rank_h2d = [round(x, 1) for x in dist.gather(h2d / h2d_ms / 1e6)]
+    rank_d2h = [round(x, 1) for x in dist.gather(d2h / d2h_ms / 1e6)]
+    rank_ms = [round(x, 3) for x in dist.gather(dt / steps * 1e3)]
     for h in hs:
         h.close()
     return {"value": round(px_per_step_all * steps / dt / 1e6, 1), "unit": "Mpix/s",
@@ -648,6 +668,8 @@ def run_e2e(pkg, torch, dist, sampler, args, rows, row0, full_h, width, octs, my
             "steps": steps, "ms_per_step": round(dt / steps * 1e3, 4),
             "h2d_ms_per_frame": round(h2d_ms, 4), "d2h_ms_per_frame": round(d2h_ms, 4),
             "h2d_GBps": round(h2d / h2d_ms / 1e6, 1), "d2h_GBps": round(d2h / d2h_ms / 1e6, 1),
+            "per_rank": {"h2d_GBps": rank_h2d, "d2h_GBps": rank_d2h, "ms_per_step": rank_ms,
+                         "note": "copy rates of one frame per rank, all ranks copying at the same time"},
             "api": "sspyr_upload + sspyr_build + sspyr_download_inplace per frame, pinned host buffers, "
                    "2 handles / 2 streams ping-pong", "result": "reference in-place layout (S+2 DoG + top Gaussian)",
             "checksum": checksum}

@@ -72,6 +72,13 @@ struct ConvParams {
     unsigned* seg_pub;                  // this level's counters, frame 0 of the launch: [segment][strip]
     const unsigned* seg_dep;            // the previous level's counters (same geometry)
     unsigned seg_frame_stride;          // counters between consecutive frame slots
+    // ... across a band seam (row bands over peer memory, chained levels): the previous level's counters of the NEIGHBOUR
+    // bands, read through the peer mapping.  The first segment row of this band also waits for the neighbour-above's
+    // segment rows [peer_up_first, peer_up_nsegs) (they hold its last R rows), the last one for the neighbour-below's row 0.
+    const unsigned* peer_seg_up;
+    const unsigned* peer_seg_dn;
+    int peer_up_first, peer_up_nsegs;
+    int seg_sys;                        // publish seg_pub with system scope (a neighbour GPU acquires it)
     int src_evict_first;                // strip kernel, TMA staging: load the source plane with an L2 evict-first policy
     float taps[2 * 32 + 1];             // taps[k + R], k = -R..R
 };

@@ -1,5 +1,6 @@
 // csrc/conv_launch.cu -- host side of CONV mode: per-level launches of conv_kernel.cuh, the decimation chain
 // between octaves, row-band halo staging, and the DoG extremum scan.  Also the halo part of the C ABI.
+#include <algorithm>
 #include <cstring>
 
 #include <cudaTypedefs.h>
@@ -216,19 +217,42 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     const bool peered_any = h->peer[0].attached || h->peer[1].attached;
     const int seg_rows = march_seg_rows(g.H, g.W, count, sms, h->tune.conv_waves, h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32);
     const long long ctas = march_ctas(g.H, g.W, count, seg_rows);
-    // Level chaining (whole-pyramid builds of an unbanded handle): the strip kernels of one octave count finished
-    // segments; a level whose source plane was produced by a chained strip kernel of the same octave (same grid)
-    // waits per segment instead of per grid.  The first level of a chain -- octave 0 level 0 from the raw frame,
-    // or level 1 of a later octave, whose base comes from the octave above through an event -- keeps the grid-wide
-    // dependency.  Only grids of more than one wave are chained (level_chained, conv_sched.h).
-    if (chain && march && h->d_seg && level_chained(h->tune.conv_chain, ctas, sms) && !peered_any && !conv_has_up(h) &&
-        !conv_has_down(h)) {
+    // Level chaining (whole-pyramid builds): the strip kernels of one octave count finished segments; a level whose
+    // source plane was produced by a chained strip kernel of the same octave (same grid) waits per segment instead of
+    // per grid.  The first level of a chain -- octave 0 level 0 from the raw frame, or level 1 of a later octave, whose
+    // base comes from the octave above through an event -- keeps the grid-wide dependency.  Only grids of more than one
+    // wave are chained (level_chained, conv_sched.h).  Row bands chain too once BOTH their neighbours are attached over
+    // peer memory with counters of their own: the seam is one more segment boundary (peer_seg_up / peer_seg_dn), the
+    // whole-level progress flags then only order a level that starts a chain and the builds of a slot among each other.
+    const bool band = conv_has_up(h) || conv_has_down(h);
+    const bool band_chains = band && (!conv_has_up(h) || (h->peer[0].attached && h->peer[0].seg)) &&
+                             (!conv_has_down(h) || (h->peer[1].attached && h->peer[1].seg)) && h->tune.conv_band_chain != 0;
+    bool chained_dep = false;
+    if (chain && march && h->d_seg && level_chained(h->tune.conv_chain, ctas, sms) && (!band || band_chains)) {
         unsigned* lv0 = h->d_seg + (size_t)first * h->seg_frame_stride + h->seg_off[octave];
         P.seg_pub = lv0 + (size_t)level * h->seg_cap[octave];
         P.seg_frame_stride = (unsigned)h->seg_frame_stride;
+        P.seg_sys = band ? 1 : 0;
         const bool src_same_octave = level >= 2 || (level == 1 && octave == 0);
-        if (src_same_octave && level_marches(h, level - 1) && h->tune.pdl != 0)
+        if (src_same_octave && level_marches(h, level - 1) && h->tune.pdl != 0) {
             P.seg_dep = lv0 + (size_t)(level - 1) * h->seg_cap[octave];
+            chained_dep = true;
+            const int Rl = h->conv[level].radius;
+            const int strips = (g.W + CONV_TW - 1) / CONV_TW;
+            if (h->peer[0].attached) {                        // the band above: the segment rows that hold its last R rows
+                const sspyr_ctx::Peer& q = h->peer[0];
+                const int nrows = march_seg_rows(q.H[octave], g.W, count, sms, h->tune.conv_waves, h->tune.conv_seg_min > 0 ? h->tune.conv_seg_min : 32);
+                P.peer_seg_up = q.seg + (size_t)first * q.seg_frame_stride + q.seg_off[octave] + (size_t)(level - 1) * q.seg_cap[octave];
+                P.peer_up_nsegs = (q.H[octave] + nrows - 1) / nrows;
+                P.peer_up_first = std::max(0, (q.H[octave] - Rl) / nrows);
+                if (P.peer_up_nsegs - P.peer_up_first > 2) P.peer_up_first = P.peer_up_nsegs - 2;   // (32-row segments, R <= 12: two rows at most)
+                (void)strips;
+            }
+            if (h->peer[1].attached) {                        // the band below: its first segment row holds its first R rows
+                const sspyr_ctx::Peer& q = h->peer[1];
+                P.peer_seg_dn = q.seg + (size_t)first * q.seg_frame_stride + q.seg_off[octave] + (size_t)(level - 1) * q.seg_cap[octave];
+            }
+        }
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
         P.src_evict_first = h->tune.conv_l2hint != 0 && level >= 1;
     }
@@ -254,14 +278,14 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     const unsigned need = (unsigned)((level == 1 && octave > 0) ? S : level - 1) + 1;   // relative to the build
     const bool fused_sync = peered && march && h->tune.conv_fused_sync != 0;
     if (fused_sync) {
-        if (!first_level) {
+        if (!first_level && !chained_dep) {                  // (a chained level waits per segment, also across the seam)
             P.wait_up = h->peer[0].attached ? h->peer[0].flag + peer_block + wo : nullptr;
             P.wait_dn = h->peer[1].attached ? h->peer[1].flag + peer_block + wo : nullptr;
             P.wait_need = need;
         }
         P.signal_flag = my_flags + octave;
         P.signal_value = (unsigned)level + 1;
-        P.done_count = my_flags + 32 + octave;
+        P.done_count = my_flags + CONV_FLAG_DONE + 16 * octave + level;
         P.epoch = epoch;
         P.timeout_mark = h->d_flag + CONV_FLAG_TIMEOUT;
     } else if (peered && !first_level) {
@@ -271,7 +295,8 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 ++*launches;
             }
     }
-    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, tm, seg_rows, h->tune.pdl != 0 && !peered_any)   // (PDL on peered launches measured slightly slower)
+    // (PDL on peered launches measured slightly slower -- except along a chain, which only exists through it)
+    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, tm, seg_rows, h->tune.pdl != 0 && (!peered_any || P.seg_pub != nullptr))
                           : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
     if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {

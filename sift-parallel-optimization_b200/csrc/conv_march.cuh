@@ -195,41 +195,62 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     // Row bands over peer memory: CTAs are dispatched in blockIdx order, so the two segments at the band edges --
     // the only ones that wait for a neighbour GPU -- are mapped to the LAST y indices: they start when the interior
     // is already under way (the neighbour has usually published by then) and never keep interior CTAs off the SMs.
-    const int seg = (P.wait_up || P.wait_dn) ? (int)((blockIdx.y + 1) % gridDim.y) : (int)blockIdx.y;
+    const bool edge_last = P.wait_up || P.wait_dn || P.peer_seg_up || P.peer_seg_dn;
+    const int seg = edge_last ? (int)((blockIdx.y + 1) % gridDim.y) : (int)blockIdx.y;
     const int y_begin = seg * seg_rows;
     const size_t fz = blockIdx.z;
     // Programmatic dependent launch along the level chain.
-    //   * no segment counters (row bands, tile-kernel neighbours): the next level may be scheduled while this one
+    //   * no segment counters (tile-kernel neighbours, stepwise builds): the next level may be scheduled while this one
     //     drains; it reads nothing this kernel writes before its own griddepcontrol.wait returns, i.e. before this
     //     grid has completed and flushed.
     //   * level chaining (seg_pub set): every CTA counts the builds of its (strip, segment) in seg_pub when its rows
     //     are written.  A level with seg_dep does NOT wait for the previous grid: each CTA waits only for the up to
     //     3x3 segments of the previous level that its tile + halo reads, so consecutive levels overlap (no idle
-    //     tail between them, and the rows just written are still in L2).  The first level of a chain keeps the
-    //     grid-wide wait and lets its dependents go only AFTER it: a chained CTA can then never run before the
-    //     previous build of these planes has completed (own counter final, nobody still reading what it overwrites).
-    //     Dependents are scheduled only once every CTA of this grid has started, so a waiting CTA's producers are
-    //     always resident or done: no deadlock.
+    //     tail between them, and the rows just written are still in L2).  On a row band whose neighbours are attached,
+    //     the first / last segment row additionally waits for the neighbour band's last / first segment rows of the
+    //     previous level, through the peer mapping (system scope): the seam is just one more segment boundary.
+    //     The first level of a chain keeps the grid-wide wait and lets its dependents go only AFTER it: a chained CTA can
+    //     then never run before the previous build of these planes has completed (own counter final, nobody still
+    //     reading what it overwrites).  Dependents are scheduled only once every CTA of this grid has started, so a
+    //     waiting CTA's producers are always resident or done (or run on another GPU): no deadlock.
     unsigned seg_next = 0;
-    const size_t seg_idx = fz * P.seg_frame_stride + (size_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const size_t seg_idx = fz * P.seg_frame_stride + (size_t)seg * gridDim.x + blockIdx.x;
     if (P.seg_dep) {
         asm volatile("griddepcontrol.launch_dependents;");
         if (tid < 32) {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seg_next) : "l"(P.seg_pub + seg_idx) : "memory");
             seg_next += 1;
+            // lanes 0..8: the 3x3 segments of this band; 9..14: neighbour-above (up to 2 segment rows x 3 strips);
+            // 15..17: neighbour-below (its first segment row x 3 strips)
+            const unsigned* f = nullptr;
+            bool sys = false;
             if (tid < 9) {
-                const int sx = (int)blockIdx.x + tid % 3 - 1, sy = (int)blockIdx.y + tid / 3 - 1;
-                if (sx >= 0 && sx < (int)gridDim.x && sy >= 0 && sy < (int)gridDim.y) {
-                    const unsigned* f = P.seg_dep + fz * P.seg_frame_stride + (size_t)sy * gridDim.x + sx;
-                    const long long t0 = clock64();
-                    for (;;) {
-                        unsigned v;
-                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
-                        if ((int)(v - seg_next) >= 0) break;
-                        if (*reinterpret_cast<volatile unsigned*>(P.timeout_mark) != 0) break;     // someone gave up: do not pile up waits
-                        if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = seg_next | 0x80000000u; break; }
-                        __nanosleep(64);
-                    }
+                const int sx = (int)blockIdx.x + tid % 3 - 1, sy = seg + tid / 3 - 1;
+                if (sx >= 0 && sx < (int)gridDim.x && sy >= 0 && sy < (int)gridDim.y)
+                    f = P.seg_dep + fz * P.seg_frame_stride + (size_t)sy * gridDim.x + sx;
+            } else if (tid < 15) {
+                const int q = tid - 9, sx = (int)blockIdx.x + q % 3 - 1, sy = P.peer_up_first + q / 3;
+                if (P.peer_seg_up && seg == 0 && sx >= 0 && sx < (int)gridDim.x && sy < P.peer_up_nsegs) {
+                    f = P.peer_seg_up + (size_t)sy * gridDim.x + sx;
+                    sys = true;
+                }
+            } else if (tid < 18) {
+                const int sx = (int)blockIdx.x + (tid - 15) - 1;
+                if (P.peer_seg_dn && (seg + 1) * seg_rows + R > P.H && sx >= 0 && sx < (int)gridDim.x) {   // halo reaches below the band
+                    f = P.peer_seg_dn + sx;
+                    sys = true;
+                }
+            }
+            if (f) {
+                const long long t0 = clock64();
+                for (;;) {
+                    unsigned v;
+                    if (sys) asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    else asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                    if ((int)(v - seg_next) >= 0) break;
+                    if (*reinterpret_cast<volatile unsigned*>(P.timeout_mark) != 0) break;     // someone gave up: do not pile up waits
+                    if (clock64() - t0 > 4000000000LL) { *P.timeout_mark = seg_next | 0x80000000u; break; }
+                    __nanosleep(64);
                 }
             }
             __syncwarp();
@@ -494,7 +515,12 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         if (tid == 0) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.seg_pub + seg_idx), "r"(seg_next) : "memory");
+            if (P.seg_sys) {                              // a neighbour GPU acquires this counter through the peer mapping
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.seg_pub + seg_idx), "r"(seg_next) : "memory");
+            } else {
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(P.seg_pub + seg_idx), "r"(seg_next) : "memory");
+            }
         }
     }
     // Fused completion signal: the last CTA of the grid publishes "this level of this octave is written"

@@ -360,7 +360,21 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
     h->in_pitch_bytes = round_up(in_row, 128);
     h->in_frame_bytes = round_up(h->in_pitch_bytes * cfg.height + 128, 256);
     auto dmalloc = [&](void** p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 256); };
-    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * (h->frame_floats * cfg.frames + (size_t)CONV_FLAG_BLOCK * cfg.frames))) != cudaSuccess ||
+    // CONV: one build counter per (frame slot, octave, level, 128-column strip, 32-row block) -- level chaining
+    // (conv_march.cuh), cascade items (conv_cascade.cuh).  They live INSIDE the output allocation, behind the progress
+    // flags, so that a neighbour band reads them through the same CUDA-IPC mapping as the planes.
+    size_t seg_words = 0;
+    if (cfg.mode == SSPYR_MODE_CONV) {
+        size_t n = 0;
+        for (int o = 0; o < h->octaves; ++o) {
+            h->seg_off[o] = n;
+            h->seg_cap[o] = (size_t)((h->oct[o].W + 127) / 128) * (size_t)((h->oct[o].H + 31) / 32);
+            n += h->seg_cap[o] * nl;
+        }
+        h->seg_frame_stride = n;
+        if (n * cfg.frames < (1ull << 31)) seg_words = n * cfg.frames;
+    }
+    if ((e = dmalloc((void**)&h->d_out, sizeof(float) * (h->frame_floats * cfg.frames + (size_t)CONV_FLAG_BLOCK * cfg.frames + seg_words))) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_in, h->in_frame_bytes * cfg.frames)) != cudaSuccess ||
         (e = dmalloc((void**)&h->d_tables, sizeof(float) * h->h_tables.size())) != cudaSuccess) {
         cudaGetLastError();
@@ -386,21 +400,6 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (halo): ") + cudaGetErrorString(e));
         }
     }
-    if (cfg.mode == SSPYR_MODE_CONV && !banded) {           // level-chaining counters (conv_march.cuh)
-        size_t n = 0;
-        for (int o = 0; o < h->octaves; ++o) {
-            h->seg_off[o] = n;
-            h->seg_cap[o] = (size_t)((h->oct[o].W + 127) / 128) * (size_t)((h->oct[o].H + 31) / 32);
-            n += h->seg_cap[o] * nl;
-        }
-        h->seg_frame_stride = n;
-        const size_t bytes = sizeof(unsigned) * n * cfg.frames;
-        if (n * cfg.frames < (1ull << 31) &&
-            ((e = dmalloc((void**)&h->d_seg, bytes)) != cudaSuccess || (e = cudaMemset(h->d_seg, 0, bytes)) != cudaSuccess)) {
-            cudaGetLastError();
-            return bail(SSPYR_ERR_NOMEM, std::string("cudaMalloc (segment counters): ") + cudaGetErrorString(e));
-        }
-    }
     if (cfg.outputs & SSPYR_OUT_EXTREMA) {
         if ((e = dmalloc((void**)&h->d_ext, h->ext_frame_bytes * cfg.frames)) != cudaSuccess) {
             cudaGetLastError();
@@ -421,6 +420,11 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
                 return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
     }
     h->d_flag = reinterpret_cast<unsigned*>(h->d_out + h->frame_floats * cfg.frames);   // inside d_out: one IPC handle covers it
+    if (seg_words) {
+        h->d_seg = h->d_flag + (size_t)CONV_FLAG_BLOCK * cfg.frames;
+        if ((e = cudaMemset(h->d_seg, 0, sizeof(unsigned) * seg_words)) != cudaSuccess)
+            return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
+    }
     h->build_seq.assign(cfg.frames, 0);
     if ((e = cudaMemset(h->d_flag, 0, (size_t)CONV_FLAG_BLOCK * cfg.frames * sizeof(float))) != cudaSuccess)
         return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
@@ -457,7 +461,6 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_tables) cudaFree(h->d_tables);
     if (h->d_halo) cudaFree(h->d_halo);
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
-    if (h->d_seg) cudaFree(h->d_seg);
     conv_drop_graphs(h);
     conv_cascade_free(h);
     destroy_lanes(h);
@@ -861,7 +864,8 @@ struct IpcBlob {                              // what a neighbour needs to read 
     uint32_t magic, bytes;
     int32_t height, width, octaves, nl, frames, pixel_type, mode, pad;
     uint64_t frame_floats, in_frame_bytes, in_pitch_bytes, flag_off_floats;
-    struct { int32_t H, pitch; uint64_t off, plane; } oct[SSPYR_MAX_OCTAVES];
+    uint64_t seg_off_words, seg_frame_stride;          // segment counters: offset from the flags, counters per slot (0: none)
+    struct { int32_t H, pitch; uint64_t off, plane, seg_off, seg_cap; } oct[SSPYR_MAX_OCTAVES];
     cudaIpcMemHandle_t out, in;
 };
 static_assert(sizeof(IpcBlob) <= SSPYR_IPC_BLOB_BYTES, "blob too large");
@@ -893,8 +897,11 @@ int sspyr_ipc_export(sspyr_handle h, void* blob, size_t capacity, size_t* bytes)
     b.frames = h->cfg.frames; b.pixel_type = h->cfg.pixel_type; b.mode = h->cfg.mode;
     b.frame_floats = h->frame_floats; b.in_frame_bytes = h->in_frame_bytes; b.in_pitch_bytes = h->in_pitch_bytes;
     b.flag_off_floats = h->frame_floats * h->cfg.frames;
+    b.seg_off_words = (uint64_t)CONV_FLAG_BLOCK * h->cfg.frames;
+    b.seg_frame_stride = h->d_seg ? h->seg_frame_stride : 0;
     for (int o = 0; o < h->octaves; ++o) {
         b.oct[o].H = h->oct[o].H; b.oct[o].pitch = h->oct[o].pitch; b.oct[o].off = h->oct[o].off; b.oct[o].plane = h->oct[o].plane;
+        b.oct[o].seg_off = h->seg_off[o]; b.oct[o].seg_cap = h->seg_cap[o];
     }
     CU(h, cudaIpcGetMemHandle(&b.out, h->d_out));
     CU(h, cudaIpcGetMemHandle(&b.in, h->d_in));
@@ -919,10 +926,15 @@ int sspyr_ipc_attach(sspyr_handle h, int side, const void* blob, size_t bytes) {
     q.out = static_cast<const float*>(q.ipc_out);
     q.in = static_cast<const unsigned char*>(q.ipc_in);
     q.flag = reinterpret_cast<const unsigned*>(q.out + b.flag_off_floats);
+    q.seg = b.seg_frame_stride ? q.flag + b.seg_off_words : nullptr;
+    q.seg_frame_stride = b.seg_frame_stride;
     q.height = b.height;
     q.frame_floats = b.frame_floats;
     q.in_frame_bytes = b.in_frame_bytes;
-    for (int o = 0; o < h->octaves; ++o) { q.H[o] = b.oct[o].H; q.off[o] = b.oct[o].off; q.plane[o] = b.oct[o].plane; }
+    for (int o = 0; o < h->octaves; ++o) {
+        q.H[o] = b.oct[o].H; q.off[o] = b.oct[o].off; q.plane[o] = b.oct[o].plane;
+        q.seg_off[o] = b.oct[o].seg_off; q.seg_cap[o] = b.oct[o].seg_cap;
+    }
     q.attached = true;
     return SSPYR_OK;
 }
@@ -942,10 +954,15 @@ int sspyr_peer_attach_local(sspyr_handle h, int side, sspyr_handle n) {
     q.out = n->d_out;
     q.in = n->d_in;
     q.flag = n->d_flag;
+    q.seg = n->d_seg;
+    q.seg_frame_stride = n->seg_frame_stride;
     q.height = n->cfg.height;
     q.frame_floats = n->frame_floats;
     q.in_frame_bytes = n->in_frame_bytes;
-    for (int o = 0; o < h->octaves; ++o) { q.H[o] = n->oct[o].H; q.off[o] = n->oct[o].off; q.plane[o] = n->oct[o].plane; }
+    for (int o = 0; o < h->octaves; ++o) {
+        q.H[o] = n->oct[o].H; q.off[o] = n->oct[o].off; q.plane[o] = n->oct[o].plane;
+        q.seg_off[o] = n->seg_off[o]; q.seg_cap[o] = n->seg_cap[o];
+    }
     q.local = true;
     q.same_device = n->device == h->device;
     q.attached = true;
@@ -978,6 +995,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_waves")) h->tune.conv_waves = value;
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
+    else if (!std::strcmp(key, "conv_band_chain")) h->tune.conv_band_chain = value;
     else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
     else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;
     else if (!std::strcmp(key, "conv_casc_debug")) h->tune.conv_casc_debug = value;

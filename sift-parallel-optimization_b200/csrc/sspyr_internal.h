@@ -16,8 +16,11 @@ namespace sspyr {
 
 struct CascMaps;                          // conv_cascade.cuh: per-octave tensor maps of the cascade kernel
 
-constexpr int CONV_FLAG_BLOCK = 64;       // CONV peer counters per frame slot: slot f uses d_flag[64 f ..): [0..15] per-octave
-                                          // progress, [32..47] finished-CTA counts ([16] of slot 0: wait-timeout marker)
+constexpr int CONV_FLAG_BLOCK = 512;      // CONV counters per frame slot: slot f uses d_flag[512 f ..): [0..15] per-octave progress,
+                                          // [16] of slot 0: wait-timeout marker, [48..51] build epochs (cascade / bands),
+                                          // [256 + 16 octave + level] finished-CTA counts of a level (levels of an octave overlap
+                                          // when they are chained, so every level counts its own CTAs)
+constexpr int CONV_FLAG_DONE = 256;
 
 // ---- per-octave geometry of one frame slot -------------------------------------------------------
 struct OctGeom {
@@ -76,6 +79,8 @@ struct Tuning {
                                // which is also the only path for row bands)
     int conv_casc_seg = 0;     // cascade: segment height in rows (0 = automatic, cascade_seg_rows)
     int conv_casc_debug = 0;   // cascade timing experiments (WRONG results): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
+    int conv_band_chain = 1;   // CONV row bands over peer memory: chain levels across the band seam through the neighbours'
+                               // segment counters (0 = whole-level progress flags between all levels, the round-1 protocol)
     int conv_chain = 1;        // CONV strip kernel: consecutive levels of an octave overlap -- a level's CTA starts as soon
                                // as the segments of the previous level it reads are published (per-segment counters),
                                // instead of after the whole previous grid (0 = grid-wide dependency only)
@@ -126,6 +131,8 @@ struct sspyr_ctx {
         const float* out = nullptr;              // neighbour's d_out
         const unsigned char* in = nullptr;       // neighbour's d_in
         const unsigned* flag = nullptr;          // neighbour's progress counter
+        const unsigned* seg = nullptr;           // neighbour's segment build counters (level chaining across the band seam)
+        size_t seg_frame_stride = 0, seg_off[SSPYR_MAX_OCTAVES] = {0}, seg_cap[SSPYR_MAX_OCTAVES] = {0};
         void* ipc_out = nullptr;                 // cudaIpcOpenMemHandle results (closed in destroy)
         void* ipc_in = nullptr;
         int height = 0, H[SSPYR_MAX_OCTAVES] = {0};
@@ -134,7 +141,7 @@ struct sspyr_ctx {
     } peer[2];                                   // [0] = band above, [1] = band below
     unsigned* d_flag = nullptr;                  // per-octave progress counters + timeout marker (inside d_out's allocation)
     // CONV level chaining: one build counter per (frame slot, octave, level, segment of a strip), see conv_march.cuh
-    unsigned* d_seg = nullptr;
+    unsigned* d_seg = nullptr;                   // (inside d_out's allocation, behind d_flag)
     size_t seg_frame_stride = 0;                 // counters per frame slot
     size_t seg_off[SSPYR_MAX_OCTAVES] = {0};     // first counter of an octave inside a slot
     size_t seg_cap[SSPYR_MAX_OCTAVES] = {0};     // counters per level of that octave (strips x ceil(H/32))
