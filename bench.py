@@ -74,6 +74,7 @@ def parse_args():
     ap.add_argument("--slots", type=int, default=0, help="frame slots in the ring (0 = enough to cover 4x L2, 2..8)")
     ap.add_argument("--tune", default="", help="rows_per_thread=2,block=256,bx=0,pdl=1")
     ap.add_argument("--extras-tune", default="", help="tuning applied to the extra records only (A/B runs)")
+    ap.add_argument("--extras-slots", type=int, default=0, help="frame slots of the extra records (A/B runs)")
     return ap.parse_args()
 
 
@@ -541,7 +542,7 @@ def run_extras(pkg, torch, dist, sampler, args, world, rank, local) -> dict:
         try:
             t0 = time.perf_counter()
             r = measure(pkg, torch, dist, sampler, wl, mode, "all", world, rank, local, steps, warm, halo=args.halo,
-                        tune=args.extras_tune, per_step_pass=False)
+                        tune=args.extras_tune, slots_arg=args.extras_slots, per_step_pass=False)
             rec = slim(r)
             dist.barrier()
             n1 = None

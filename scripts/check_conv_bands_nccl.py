@@ -77,37 +77,45 @@ def main() -> int:
     # peer memory, three frame slots in flight, several rounds back to back (from the third build of a slot on the launch
     # sequence replays as a CUDA graph).  Every band must equal the UNBANDED build of the same pixels on its own GPU bit for
     # bit, and no wait may have timed out (sspyr_sync reports that).
+    # Both seam protocols: whole-level progress flags (default) and levels chained across the seam through the neighbours'
+    # segment counters (conv_band_chain = 1).
     if "--c4" in sys.argv:
         H, W, O5, slots = 4320, 7680, 5, 3
         r0, nr = pkg.band_rows(H, O5, world, rank)
-        band = pkg.ScaleSpace(nr, W, O5, S, mode=pkg.MODE_CONV, device=local, band_row0=r0, full_height=H, frames=slots)
-        band.set_stream(torch.cuda.current_stream().cuda_stream)
-        link = pkg.PeerExchanger(band, rank, world)
         whole = pkg.ScaleSpace(H, W, O5, S, mode=pkg.MODE_CONV, device=local)
-        try:
-            for rnd in range(4):
-                imgs = [pkg.synth.noise(H, W, frame=100 * rnd + f) for f in range(slots)]
-                for f in range(slots):
-                    band.upload(np.ascontiguousarray(imgs[f][r0:r0 + nr]), frame=f)
-                band.sync()
-                dist.barrier()                               # every band's pixels are in place before anyone reads a halo
-                for f in range(slots):                       # nothing waits between these calls
-                    link.build(f)
-                band.sync()                                  # raises if a neighbour / level wait timed out
-                dist.barrier()
-                if rnd in (0, 3):
-                    for f in (0, slots - 1):
-                        whole.upload(imgs[f])
-                        whole.build()
-                        wg, wd = whole.download_gauss(), whole.download_dog()
-                        bg, bd = band.download_gauss(f), band.download_dog(f)
-                        for o in range(O5):
-                            lo, n = r0 >> o, nr >> o
-                            ok &= bool(np.array_equal(bg[o], wg[o][:, lo:lo + n])) and bool(np.array_equal(bd[o], wd[o][:, lo:lo + n]))
-                dist.barrier()
-        finally:
-            band.close()
-            whole.close()
+        want = {}
+        for chain in (0, 1):
+            band = pkg.ScaleSpace(nr, W, O5, S, mode=pkg.MODE_CONV, device=local, band_row0=r0, full_height=H, frames=slots)
+            band.set_stream(torch.cuda.current_stream().cuda_stream)
+            band.set_tuning(conv_band_chain=chain)
+            link = pkg.PeerExchanger(band, rank, world)
+            try:
+                for rnd in range(4):
+                    imgs = [pkg.synth.noise(H, W, frame=100 * rnd + f) for f in range(slots)] if rnd in (0, 3) else imgs
+                    for f in range(slots):
+                        band.upload(np.ascontiguousarray(imgs[f][r0:r0 + nr]), frame=f)
+                    band.sync()
+                    dist.barrier()                           # every band's pixels are in place before anyone reads a halo
+                    for f in range(slots):                   # nothing waits between these calls
+                        link.build(f)
+                    band.sync()                              # raises if a neighbour / level wait timed out
+                    dist.barrier()
+                    if rnd in (0, 3):
+                        for f in (0, slots - 1):
+                            key = (rnd, f)
+                            if key not in want:
+                                whole.upload(imgs[f])
+                                whole.build()
+                                want[key] = (whole.download_gauss(), whole.download_dog())
+                            wg, wd = want[key]
+                            bg, bd = band.download_gauss(f), band.download_dog(f)
+                            for o in range(O5):
+                                lo, n = r0 >> o, nr >> o
+                                ok &= bool(np.array_equal(bg[o], wg[o][:, lo:lo + n])) and bool(np.array_equal(bd[o], wd[o][:, lo:lo + n]))
+                    dist.barrier()
+            finally:
+                band.close()
+        whole.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     print(f"rank {rank}/{world} band rows [{row0},{row0 + rows}) CONV max|err|={worst:.3g} "

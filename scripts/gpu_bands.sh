@@ -9,7 +9,7 @@ if [ "${TEST:-1}" = "1" ]; then
   if [ $rc -ne 0 ]; then echo "check failed: no bench"; exit 1; fi
 fi
 for bc in ${BCS:-1 0}; do
-  timeout ${BT:-150} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2972$bc bench.py --gpus $N --no-e2e --no-cpu-baseline --steps 2 --warmup 3 --extras ${EXTRAS:-c4_conv_rowband,c5_conv_rowband} --extras-tune conv_band_chain=$bc > $O/bench_bc$bc.json 2> $O/bench_bc$bc.err; echo "bench bc=$bc rc=$?"
+  timeout ${BT:-150} python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2972$bc bench.py --gpus $N --no-e2e --no-cpu-baseline --steps 2 --warmup 3 --extras ${EXTRAS:-c4_conv_rowband,c5_conv_rowband} --extras-tune conv_band_chain=$bc${XT:-} ${XA:-} > $O/bench_bc$bc.json 2> $O/bench_bc$bc.err; echo "bench bc=$bc rc=$?"
   python - $O/bench_bc$bc.json <<'PY'
 import json,sys
 try:

@@ -78,7 +78,7 @@ struct ConvParams {
     const unsigned* peer_seg_up;
     const unsigned* peer_seg_dn;
     int peer_up_first, peer_up_nsegs;
-    int seg_sys;                        // publish seg_pub with system scope (a neighbour GPU acquires it)
+    int seg_sys;                        // bit 0 / 1: a band above / below acquires the counters of this band's first / last segment rows
     int src_evict_first;                // strip kernel, TMA staging: load the source plane with an L2 evict-first policy
     float taps[2 * 32 + 1];             // taps[k + R], k = -R..R
 };

@@ -232,7 +232,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
         unsigned* lv0 = h->d_seg + (size_t)first * h->seg_frame_stride + h->seg_off[octave];
         P.seg_pub = lv0 + (size_t)level * h->seg_cap[octave];
         P.seg_frame_stride = (unsigned)h->seg_frame_stride;
-        P.seg_sys = band ? 1 : 0;
+        P.seg_sys = (conv_has_up(h) ? 1 : 0) | (conv_has_down(h) ? 2 : 0);
         const bool src_same_octave = level >= 2 || (level == 1 && octave == 0);
         if (src_same_octave && level_marches(h, level - 1) && h->tune.pdl != 0) {
             P.seg_dep = lv0 + (size_t)(level - 1) * h->seg_cap[octave];

@@ -515,7 +515,9 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         if (tid == 0) {
             asm volatile("fence.proxy.async.global;" ::: "memory");
             __threadfence();
-            if (P.seg_sys) {                              // a neighbour GPU acquires this counter through the peer mapping
+            // a neighbour GPU acquires the counters of the band's first segment row (seg_sys & 1: a band above exists) and
+            // of the rows that hold its last 12 rows (seg_sys & 2: a band below exists): those are released at system scope
+            if (((P.seg_sys & 1) && seg == 0) || ((P.seg_sys & 2) && (seg + 1) * seg_rows + 12 > P.H)) {
                 __threadfence_system();
                 asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(P.seg_pub + seg_idx), "r"(seg_next) : "memory");
             } else {

@@ -136,7 +136,10 @@ cudaError_t mark_tail(sspyr_ctx* h) {
 int lane_count(const sspyr_ctx* h) {
     if (h->cfg.mode != SSPYR_MODE_CONV || h->tune.timing) return 1;
     // (bands driven level by level from the host -- no peers attached -- never come here)
-    return frame_lanes(h->tune.conv_lanes, h->cfg.frames, h->cfg.full_height != h->cfg.height);
+    const bool banded = h->cfg.full_height != h->cfg.height;
+    if (banded && h->tune.conv_band_lanes > 3)               // explicit request for more band builds in flight than the default 3
+        return std::min(std::min(h->tune.conv_band_lanes, h->cfg.frames), 16);
+    return frame_lanes(h->tune.conv_lanes, h->cfg.frames, banded);
 }
 
 cudaError_t ensure_lanes(sspyr_ctx* h, int n) {
@@ -996,6 +999,7 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
     else if (!std::strcmp(key, "conv_band_chain")) h->tune.conv_band_chain = value;
+    else if (!std::strcmp(key, "conv_band_lanes")) h->tune.conv_band_lanes = value;
     else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
     else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;
     else if (!std::strcmp(key, "conv_casc_debug")) h->tune.conv_casc_debug = value;
