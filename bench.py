@@ -270,7 +270,7 @@ def measure(pkg, torch, dist, sampler, wl: str, mode_name: str, outputs_name: st
     if mode_name == "conv" and part == "batch":
         slots = 8                                 # CONV launches one kernel per LEVEL for all slots of a batch call
     if mode_name == "conv" and part == "rowband" and world > 1:
-        slots = 3                                 # CONV row bands keep up to 3 builds in flight (frame lanes, per-slot counters)
+        slots = 6                                 # CONV row bands keep up to 6 builds in flight (frame lanes, per-slot counters)
     if mode_name == "conv" and part == "replica":
         slots = 8 if wl != "c1" else 64           # CONV keeps up to 8 single-frame builds in flight (frame lanes)
     if slots_arg > 0:

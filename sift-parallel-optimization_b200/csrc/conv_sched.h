@@ -143,8 +143,10 @@ inline std::vector<unsigned> cascade_item_table(const CascItemGeom* g, int octav
 }
 
 // Frame lanes: builds of different frame slots in flight at once.  Row bands reading their neighbours' planes in
-// place keep at most 3: the CTAs at a band edge spin until the neighbour GPU has published the level they read, so
-// the builds in flight must stay few enough that waiting CTAs can never fill a GPU.
+// place: the CTAs at a band edge spin until the neighbour GPU has published the level they read.  A spinning CTA waits
+// for a kernel that PRECEDES the neighbour's own spinners of that build in its stream, and whose own waits are for
+// levels this GPU has already finished, so progress never depends on a free slot here; the round-1 cap of 3 builds in
+// flight was conservative and is now only the fallback when conv_band_lanes is not set (default 6, sspyr_internal.h).
 inline int frame_lanes(int conv_lanes, int frames, bool banded) {
     int n = conv_lanes < frames ? conv_lanes : frames;
     if (banded && n > 3) n = 3;
