@@ -7,7 +7,7 @@ set -u
 mkdir -p gpurun_out
 PKG=sift-parallel-optimization_b200
 run() {  # tag, extra args
-  timeout 150 python bench.py --mode conv --no-cpu-baseline --no-e2e "${@:2}" 2>gpurun_out/ab_$1.err | python -c "
+  timeout 150 python bench.py --mode conv --no-cpu-baseline --no-e2e --no-extras "${@:2}" 2>gpurun_out/ab_$1.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print('$1', d['config']['name'], 'ms', round(d['ms_per_step'],4), 'Mpix/s', d['value'], 'frac', d['roofline']['frac'])" | tee -a gpurun_out/ab_results.txt
 }
@@ -17,7 +17,7 @@ for lib in /tmp/libsspyr_shipped.so build/libsspyr_*.so; do
   [ -f "$lib" ] || continue
   tag=$(basename $lib .so); tag=${tag#libsspyr_}
   cp $lib $PKG/libsspyr.so
-  timeout 400 python -m pytest tests/test_gpu_conv.py -m gpu -x -q > gpurun_out/ab_pytest_$tag.log 2>&1; echo "$tag pytest rc=$?" | tee -a gpurun_out/ab_results.txt; tail -1 gpurun_out/ab_pytest_$tag.log
+  timeout 400 python -m pytest tests/test_gpu_conv.py -m gpu -x -q -k "${PYK:-marching or chaining or full_pyramid or random or bands_match or scipy}" > gpurun_out/ab_pytest_$tag.log 2>&1; echo "$tag pytest rc=$?" | tee -a gpurun_out/ab_results.txt; tail -1 gpurun_out/ab_pytest_$tag.log
   for wl in ${WLS:-c4 c5 c3 c2}; do run ${tag}_$wl --workload $wl; done
 done
 cp /tmp/libsspyr_shipped.so $PKG/libsspyr.so
