@@ -547,8 +547,8 @@ def run_extras(pkg, torch, dist, sampler, args, world, rank, local) -> dict:
             dist.barrier()
             n1 = None
             if rank == 0:                         # the same workload on ONE GPU, same run, same box: the speed-up's denominator
-                r1 = measure(pkg, torch, Solo(), sampler, wl, mode, "all", 1, 0, local, max(2, steps // 2), warm,
-                             per_step_pass=False)
+                r1 = max((measure(pkg, torch, Solo(), sampler, wl, mode, "all", 1, 0, local, max(3, steps // 2), warm,
+                                  per_step_pass=False) for _ in range(2)), key=lambda r: r["value"])   # (better of two short runs)
                 n1 = {"value": r1["value"], "ms_per_step": r1["ms_per_step"], "steps": r1["steps"],
                       "roofline_frac": r1["roofline"]["frac"]}
             dist.barrier()

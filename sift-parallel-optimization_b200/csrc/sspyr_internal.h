@@ -81,8 +81,8 @@ struct Tuning {
     int conv_casc_debug = 0;   // cascade timing experiments (WRONG results): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
     int conv_band_lanes = 6;   // CONV row bands over peer memory: builds of different slots in flight (<= frame slots; measured on
                                // 8 GPUs, 8K / 16K: 3 -> 2.9x / 6.1x, 6 -> 3.6x / 6.8x, 8 -> 3.7x / 6.7x of one GPU, profiles/r2_bands.md)
-    int conv_band_split = 1;   // CONV row bands over peer memory: edge segment rows in a grid of their own behind one-thread wait
-                               // kernels (0 = edge CTAs spin inside the level kernel, the round-1 protocol)
+    int conv_band_split = 0;   // CONV row bands over peer memory: 1 = edge segment rows in a grid of their own behind one-thread wait
+                               // kernels (0, default = edge CTAs wait inside the level kernel: measured faster on 8 GPUs)
     int conv_band_chain = 0;   // CONV row bands over peer memory: chain levels across the band seam through the neighbours'
                                // segment counters (0, default = whole-level progress flags between all levels: measured
                                // 5-7 % faster on 2 GPUs, profiles/r2_bands.md)
