@@ -200,7 +200,7 @@ SSPYR_API int sspyr_window_table(sspyr_handle h, int octave, int level, int axis
 SSPYR_API int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacity, int* radius);
 /* Kernel tuning knobs (bench/sweeps): key in {"rows_per_thread","block","bx","pdl","timing","occ","prefetch_next","conv_streams",
  * "conv_march","conv_graph","conv_tma","conv_waves","conv_seg_min","conv_fused_sync","conv_chain","conv_l2hint","conv_lanes",
- * "conv_cascade","conv_casc_seg","conv_band_chain","conv_band_split","conv_band_lanes"}.  The ones that change behaviour a caller can observe:
+ * "conv_cascade","conv_casc_seg","conv_band_chain","conv_band_lanes"}.  The ones that change behaviour a caller can observe:
  *   conv_lanes      (default 8) CONV builds of different frame slots that may be in flight at once; 1 = strictly one
  *                   after the other.  Work enqueued on the handle's stream after a build always sees it complete.
  *   conv_band_lanes (default 6) the same for row bands that read their neighbours' planes over peer memory.
@@ -208,8 +208,7 @@ SSPYR_API int sspyr_conv_taps(sspyr_handle h, int level, float* dst, int capacit
  *                   starts when the previous grid has completed; 2 = chained even for grids of less than a wave.
  *   conv_cascade    (default 0) 2 = build a whole pyramid with ONE launch (all levels pipelined through L2; same bits;
  *                   measured slower than one launch per level); 1 = only for frames of >= 4 Mpixel.
- *   conv_band_chain (default 0) 1 = chain levels across a band seam through the neighbours' segment counters.
- *   conv_band_split (default 0) 1 = launch a band level as an interior grid plus an edge grid behind wait kernels. */
+ *   conv_band_chain (default 0) 1 = chain levels across a band seam through the neighbours' segment counters. */
 SSPYR_API int sspyr_set_tuning(sspyr_handle h, const char* key, int value);
 
 /* ---- row-band halo exchange (CONV mode, multi-GPU): see DESIGN.md "Row bands" ----------------------- */

@@ -15,8 +15,8 @@ cudaError_t SSPYR_CAT(launch_conv_r, SSPYR_R)(const ConvParams& P, int src_kind,
 }
 #if SSPYR_R <= 12
 cudaError_t SSPYR_CAT(launch_march_r, SSPYR_R)(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
-                                               const CUtensorMap* tmap, int seg_rows, bool pdl, int grid_segs) {
-    return launch_march_src<SSPYR_R>(P, src_kind, st, device, frames, tmap, seg_rows, pdl, grid_segs);
+                                               const CUtensorMap* tmap, int seg_rows, bool pdl) {
+    return launch_march_src<SSPYR_R>(P, src_kind, st, device, frames, tmap, seg_rows, pdl);
 }
 int SSPYR_CAT(march_box_cols_r, SSPYR_R)() { return conv_pitch_in<SSPYR_R>(); }
 #endif

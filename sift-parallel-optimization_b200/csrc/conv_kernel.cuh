@@ -79,11 +79,6 @@ struct ConvParams {
     const unsigned* peer_seg_dn;
     int peer_up_first, peer_up_nsegs;
     int seg_sys;                        // bit 0 / 1: a band above / below acquires the counters of this band's first / last segment rows
-    // A level of a row band launched as TWO grids (conv_band_split): the segment rows whose halo reaches into a neighbour
-    // band ("edge" grid, behind one-thread wait kernels) and the rest ("interior" grid, which starts at once).  The grid's
-    // blockIdx.y maps to segment  y < edge_top ? y : y + seg_shift  of nsegs_all segment rows; 0 / 0 / 0 = one grid, identity.
-    int nsegs_all, edge_top, seg_shift;
-    unsigned done_total;                // CTAs of the whole level (both grids) for the finished-CTA count; 0 = this grid's size
     int src_evict_first;                // strip kernel, TMA staging: load the source plane with an L2 evict-first policy
     float taps[2 * 32 + 1];             // taps[k + R], k = -R..R
 };

@@ -15,7 +15,7 @@ SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12) SSPYR_DECL(13) SSPYR_
 SSPYR_DECL(20) SSPYR_DECL(24) SSPYR_DECL(28) SSPYR_DECL(32)
 #undef SSPYR_DECL
 #define SSPYR_DECL(n)                                                                                  \
-    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, const CUtensorMap*, int, bool, int); \
+    cudaError_t launch_march_r##n(const ConvParams&, int, cudaStream_t, int, int, const CUtensorMap*, int, bool); \
     int march_box_cols_r##n();
 SSPYR_DECL(1) SSPYR_DECL(2) SSPYR_DECL(3) SSPYR_DECL(4) SSPYR_DECL(5) SSPYR_DECL(6) SSPYR_DECL(7) SSPYR_DECL(8)
 SSPYR_DECL(9) SSPYR_DECL(10) SSPYR_DECL(11) SSPYR_DECL(12)
@@ -86,9 +86,9 @@ cudaError_t dispatch(int rt, const ConvParams& P, int src_kind, int variant, cud
 }
 
 cudaError_t dispatch_march(int r, const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
-                           const CUtensorMap* tmap, int seg_rows, bool pdl, int grid_segs = 0) {
+                           const CUtensorMap* tmap, int seg_rows, bool pdl) {
     switch (r) {
-#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, tmap, seg_rows, pdl, grid_segs);
+#define SSPYR_CASE(n) case n: return launch_march_r##n(P, src_kind, st, device, frames, tmap, seg_rows, pdl);
         SSPYR_CASE(1) SSPYR_CASE(2) SSPYR_CASE(3) SSPYR_CASE(4) SSPYR_CASE(5) SSPYR_CASE(6) SSPYR_CASE(7) SSPYR_CASE(8)
         SSPYR_CASE(9) SSPYR_CASE(10) SSPYR_CASE(11) SSPYR_CASE(12)
 #undef SSPYR_CASE
@@ -133,25 +133,6 @@ bool make_plane_tensor_map(CUtensorMap* map, const float* plane0, int pitch, int
 }
 
 }  // namespace
-
-// Side stream + fork / join events of one octave stream (split band levels); created on first use, i.e. during the first,
-// eager build of a slot -- never while a launch sequence is being captured.
-static EdgeSet* edge_set_for(sspyr_ctx* h, cudaStream_t st) {
-    for (auto& e : h->edge_sets)
-        if (e.owner == st) return &e;
-    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) return nullptr;
-    EdgeSet e{};
-    e.owner = st;
-    if (cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e.fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e.join, cudaEventDisableTiming) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    h->edge_sets.push_back(e);
-    return &h->edge_sets.back();
-}
 
 bool conv_has_up(const sspyr_ctx* h) { return h->cfg.band_row0 > 0; }
 bool conv_has_down(const sspyr_ctx* h) { return h->cfg.band_row0 + h->cfg.height < h->cfg.full_height; }
@@ -314,54 +295,10 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 ++*launches;
             }
     }
-    // Split level (conv_band_split, whole-pyramid builds of a band over peer memory): the segment rows whose halo reaches
-    // into a neighbour band go to an "edge" grid on a side stream, behind ONE-thread wait kernels; everything else runs at
-    // once as the "interior" grid.  A CTA that spins inside the level kernel holds a quarter of an SM; with several builds in
-    // flight the spinners (2 segment rows x 60 strips per level and build on 8K) crowd out the other builds' work.
-    cudaError_t e = cudaSuccess;
-    const int nsegs = (g.H + seg_rows - 1) / seg_rows;
-    bool split = false;
-    if (chain && fused_sync && (P.wait_up || P.wait_dn) && h->tune.conv_band_split != 0 && count == 1) {
-        const int e_top = P.wait_up ? 1 : 0;
-        int e_bot = 0;
-        if (P.wait_dn)
-            for (int sg = nsegs - 1; sg >= e_top && (sg + 1) * seg_rows + R > g.H; --sg) ++e_bot;
-        const int n_int = nsegs - e_top - e_bot;
-        EdgeSet* es = (e_top + e_bot > 0 && n_int > 0) ? edge_set_for(const_cast<sspyr_ctx*>(h), st) : nullptr;
-        if (es) {
-            split = true;
-            const unsigned* wu = P.wait_up;
-            const unsigned* wd = P.wait_dn;
-            P.wait_up = P.wait_dn = nullptr;
-            P.nsegs_all = nsegs;
-            P.done_total = (unsigned)(((g.W + CONV_TW - 1) / CONV_TW) * nsegs * count);
-            if ((e = cudaEventRecord(es->fork, st)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(es->stream, es->fork, 0)) != cudaSuccess) return e;
-            for (const unsigned* w : {wu, wd})
-                if (w) {
-                    conv_wait_kernel<<<1, 1, 0, es->stream>>>(w, need, epoch, h->d_flag);
-                    ++*launches;
-                }
-            ConvParams E = P;                                // edge grid: y < e_top -> segment y, else the last e_bot segments
-            E.edge_top = e_top;
-            E.seg_shift = nsegs - e_bot - e_top;
-            if ((e = dispatch_march(R, E, src_kind, es->stream, h->device, count, tm, seg_rows, false, e_top + e_bot)) != cudaSuccess) return e;
-            ++*launches;
-            ConvParams I = P;                                // interior grid: segments e_top .. nsegs - e_bot - 1
-            I.edge_top = 0;
-            I.seg_shift = e_top;
-            if ((e = dispatch_march(R, I, src_kind, st, h->device, count, tm, seg_rows, false, n_int)) != cudaSuccess) return e;
-            ++*launches;
-            if ((e = cudaEventRecord(es->join, es->stream)) != cudaSuccess) return e;
-            if ((e = cudaStreamWaitEvent(st, es->join, 0)) != cudaSuccess) return e;
-        }
-    }
     // (PDL on peered launches measured slightly slower -- except along a chain, which only exists through it)
-    if (!split) {
-        e = march ? dispatch_march(R, P, src_kind, st, h->device, count, tm, seg_rows, h->tune.pdl != 0 && (!peered_any || P.seg_pub != nullptr))
-                  : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
-        if (e == cudaSuccess) ++*launches;
-    }
+    cudaError_t e = march ? dispatch_march(R, P, src_kind, st, h->device, count, tm, seg_rows, h->tune.pdl != 0 && (!peered_any || P.seg_pub != nullptr))
+                          : dispatch(RT, P, src_kind, variant, st, h->device, count, sms);
+    if (e == cudaSuccess) ++*launches;
     if (e == cudaSuccess && peered && !fused_sync) {
         conv_signal_kernel<<<1, 1, 0, st>>>(my_flags + octave, (unsigned)level + 1, epoch);
         ++*launches;

@@ -196,8 +196,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
     // the only ones that wait for a neighbour GPU -- are mapped to the LAST y indices: they start when the interior
     // is already under way (the neighbour has usually published by then) and never keep interior CTAs off the SMs.
     const bool edge_last = P.wait_up || P.wait_dn || P.peer_seg_up || P.peer_seg_dn;
-    const int seg = P.nsegs_all ? ((int)blockIdx.y < P.edge_top ? (int)blockIdx.y : (int)blockIdx.y + P.seg_shift)   // split level
-                                : (edge_last ? (int)((blockIdx.y + 1) % gridDim.y) : (int)blockIdx.y);
+    const int seg = edge_last ? (int)((blockIdx.y + 1) % gridDim.y) : (int)blockIdx.y;
     const int y_begin = seg * seg_rows;
     const size_t fz = blockIdx.z;
     // Programmatic dependent launch along the level chain.
@@ -532,7 +531,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
         __syncthreads();
         if (tid == 0) {
             __threadfence();
-            const unsigned total = P.done_total ? P.done_total : gridDim.x * gridDim.y * gridDim.z;
+            const unsigned total = gridDim.x * gridDim.y * gridDim.z;
             if (atomicAdd(P.done_count, 1u) == total - 1) {
                 *P.done_count = 0;                       // ready for the next launch on this octave's stream
                 __threadfence_system();
@@ -544,7 +543,7 @@ conv_strip_kernel(const __grid_constant__ ConvParams P, int seg_rows, const __gr
 
 template <int R, int SRC, bool TMA>
 cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, int frames, const CUtensorMap& tmap,
-                             int seg_rows, bool pdl, int grid_segs) {
+                             int seg_rows, bool pdl) {
     constexpr size_t smem = strip_smem_bytes<R>();
     static_assert(smem + 1024 <= (228 * 1024) / STRIP_CTAS_PER_SM, "the segmentation counts on at least 4 CTAs per SM");
     static bool configured[64] = {false};
@@ -554,7 +553,7 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
         if (device >= 0 && device < 64) configured[device] = true;
     }
     const int strips = (P.W + CONV_TW - 1) / CONV_TW;
-    const int nseg = grid_segs > 0 ? grid_segs : (P.H + seg_rows - 1) / seg_rows;   // (grid_segs: one of the two grids of a split level)
+    const int nseg = (P.H + seg_rows - 1) / seg_rows;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(strips, nseg, frames);
     cfg.blockDim = dim3(CONV_THREADS);
@@ -571,15 +570,15 @@ cudaError_t launch_march_one(const ConvParams& P, cudaStream_t st, int device, i
 // tmap: tensor map of the source plane (box = PIN columns x 32 rows x 1 frame) or nullptr -> cp.async staging
 template <int R>
 cudaError_t launch_march_src(const ConvParams& P, int src_kind, cudaStream_t st, int device, int frames,
-                             const CUtensorMap* tmap, int seg_rows, bool pdl, int grid_segs) {
+                             const CUtensorMap* tmap, int seg_rows, bool pdl) {
     static const CUtensorMap none{};
     switch (src_kind) {
-        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, none, seg_rows, pdl, grid_segs);
-        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, none, seg_rows, pdl, grid_segs);
-        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, none, seg_rows, pdl, grid_segs);
+        case SSPYR_PIXEL_I32: return launch_march_one<R, SSPYR_PIXEL_I32, false>(P, st, device, frames, none, seg_rows, pdl);
+        case SSPYR_PIXEL_F32: return launch_march_one<R, SSPYR_PIXEL_F32, false>(P, st, device, frames, none, seg_rows, pdl);
+        case SSPYR_PIXEL_U8: return launch_march_one<R, SSPYR_PIXEL_U8, false>(P, st, device, frames, none, seg_rows, pdl);
         default:
-            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, *tmap, seg_rows, pdl, grid_segs)
-                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, none, seg_rows, pdl, grid_segs);
+            return tmap ? launch_march_one<R, CONV_SRC_PLANE, true>(P, st, device, frames, *tmap, seg_rows, pdl)
+                        : launch_march_one<R, CONV_SRC_PLANE, false>(P, st, device, frames, none, seg_rows, pdl);
     }
 }
 

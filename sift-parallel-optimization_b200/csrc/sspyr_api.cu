@@ -429,7 +429,6 @@ int sspyr_create(const sspyr_config* cfg_in, sspyr_handle* out) {
             return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
     }
     h->build_seq.assign(cfg.frames, 0);
-    h->edge_sets.reserve(512);                               // (16 lanes x 16 octave streams at most)
     if ((e = cudaMemset(h->d_flag, 0, (size_t)CONV_FLAG_BLOCK * cfg.frames * sizeof(float))) != cudaSuccess)
         return bail(SSPYR_ERR_CUDA, std::string("device setup: ") + cudaGetErrorString(e));
     if ((e = cudaMemcpy(h->d_tables, h->h_tables.data(), sizeof(float) * h->h_tables.size(),
@@ -467,11 +466,6 @@ int sspyr_destroy(sspyr_handle h) {
     if (h->d_halo_raw) cudaFree(h->d_halo_raw);
     conv_drop_graphs(h);
     conv_cascade_free(h);
-    for (auto& es : h->edge_sets) {
-        if (es.stream) cudaStreamDestroy(es.stream);
-        if (es.fork) cudaEventDestroy(es.fork);
-        if (es.join) cudaEventDestroy(es.join);
-    }
     destroy_lanes(h);
     for (cudaStream_t st : h->aux) if (st) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_base) if (ev) cudaEventDestroy(ev);
@@ -1005,7 +999,6 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_seg_min")) h->tune.conv_seg_min = value;
     else if (!std::strcmp(key, "conv_chain")) h->tune.conv_chain = value;
     else if (!std::strcmp(key, "conv_band_chain")) h->tune.conv_band_chain = value;
-    else if (!std::strcmp(key, "conv_band_split")) h->tune.conv_band_split = value;
     else if (!std::strcmp(key, "conv_band_lanes")) h->tune.conv_band_lanes = value;
     else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
     else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;

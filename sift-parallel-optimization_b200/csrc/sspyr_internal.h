@@ -81,8 +81,6 @@ struct Tuning {
     int conv_casc_debug = 0;   // cascade timing experiments (WRONG results): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
     int conv_band_lanes = 6;   // CONV row bands over peer memory: builds of different slots in flight (<= frame slots; measured on
                                // 8 GPUs, 8K / 16K: 3 -> 2.9x / 6.1x, 6 -> 3.6x / 6.8x, 8 -> 3.7x / 6.7x of one GPU, profiles/r2_bands.md)
-    int conv_band_split = 0;   // CONV row bands over peer memory: 1 = edge segment rows in a grid of their own behind one-thread wait
-                               // kernels (0, default = edge CTAs wait inside the level kernel: measured faster on 8 GPUs)
     int conv_band_chain = 0;   // CONV row bands over peer memory: chain levels across the band seam through the neighbours'
                                // segment counters (0, default = whole-level progress flags between all levels: measured
                                // 5-7 % faster on 2 GPUs, profiles/r2_bands.md)
@@ -99,13 +97,6 @@ struct ConvLevel {
     size_t taps_off = 0;       // float offset in d_tables of taps[2R+1]
 };
 
-}  // namespace sspyr
-
-namespace sspyr {
-struct EdgeSet {                              // side stream of one octave stream for the edge grid of a split band level
-    cudaStream_t owner = nullptr, stream = nullptr;
-    cudaEvent_t fork = nullptr, join = nullptr;
-};
 }  // namespace sspyr
 
 // ---- the handle -----------------------------------------------------------------------------------
@@ -182,7 +173,6 @@ struct sspyr_ctx {
         unsigned seen_tail = 0;              // tail_seq the lane has already waited for
     };
     std::vector<Lane> lanes;
-    std::vector<sspyr::EdgeSet> edge_sets;   // (reserved up front: pointers into it are handed out)
     std::vector<int> slot_lane;              // lane of the latest build that wrote a slot (-1: none)
     cudaEvent_t ev_tail = nullptr;           // latest library operation on the handle's stream that a build must follow
     unsigned tail_seq = 0;
