@@ -95,7 +95,6 @@ cudaError_t launch_conv_cascade(sspyr_ctx* h, int first, int count, int* launche
     C.nl = h->nl;
     C.S = h->cfg.S;
     C.want_dog = (h->cfg.outputs & SSPYR_OUT_DOG) ? 1 : 0;
-    C.debug = h->tune.conv_casc_debug;
     CascItemGeom geom[SSPYR_MAX_OCTAVES];
     int radius[SSPYR_MAX_LEVELS];
     for (int s = 0; s < h->nl; ++s) radius[s] = cascade_radius_class(h->conv[s].radius);

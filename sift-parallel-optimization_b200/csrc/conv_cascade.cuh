@@ -69,7 +69,6 @@ struct CascParams {
     int raw_pitch, raw_kind;
     int slot0;                                // absolute index of the launch's first slot (TMA frame coordinate)
     int octaves, nl, S, want_dog;
-    int debug;                                // timing experiments only (results are wrong): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
     unsigned short bseq[CASC_MAX_FRAMES];     // per frame of the launch: builds of that slot started before this one (mod 2^16)
     CascOct oct[SSPYR_MAX_OCTAVES];
     CascLevel lev[SSPYR_MAX_LEVELS];
@@ -257,7 +256,7 @@ __device__ __forceinline__ void cascade_item(const CascParams& C, const CascMaps
             }
         }
         __syncwarp();
-        if (D.ctr && !(C.debug & 4))                      // warm-up rows + the first step's rows
+        if (D.ctr)                                        // warm-up rows + the first step's rows
             casc_wait_rows(D, b16, max(y_begin - R, 0), min(y_begin + R + TH, H), xa, xb, C.timeout_mark, lane);
     }
     __syncthreads();
@@ -313,7 +312,7 @@ __device__ __forceinline__ void cascade_item(const CascParams& C, const CascMaps
             }
         }
         if (__syncthreads_or(miss)) { lost = true; break; }   // new rows landed; carried rows in place; every thread has stored step k-1
-        if (k > 0 && tid == 0 && !(C.debug & 2)) {       // steps 0..k-1 of this item are written: publish (release is cumulative
+        if (k > 0 && tid == 0) {                         // steps 0..k-1 of this item are written: publish (release is cumulative
             st_release(own, b16 + (unsigned)k);          // over the other threads' stores, ordered before it by the barrier)
         }
         strip_row_pass<R, TH, 2 * R, PIN>(taps, sIn, sT, tid);
@@ -339,7 +338,7 @@ __device__ __forceinline__ void cascade_item(const CascParams& C, const CascMaps
         __syncthreads();
         if (k + 1 < nsteps) {                            // next step's rows: in flight during the column pass below
             const int gy0 = y_begin + R + (k + 1) * TH;
-            if (D.ctr && !(C.debug & 1)) {
+            if (D.ctr) {
                 if (tid < 32) casc_wait_rows(D, b16, min(gy0, H - 1), min(gy0 + TH, H), xa, xb, C.timeout_mark, lane);
                 if (!step_uses_tma(gy0)) __syncthreads();  // every thread stages: all of them wait for the first warp
             }

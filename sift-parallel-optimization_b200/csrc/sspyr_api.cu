@@ -1002,7 +1002,6 @@ int sspyr_set_tuning(sspyr_handle h, const char* key, int value) {
     else if (!std::strcmp(key, "conv_band_lanes")) h->tune.conv_band_lanes = value;
     else if (!std::strcmp(key, "conv_cascade")) h->tune.conv_cascade = value;
     else if (!std::strcmp(key, "conv_casc_seg")) h->tune.conv_casc_seg = value;
-    else if (!std::strcmp(key, "conv_casc_debug")) h->tune.conv_casc_debug = value;
     else if (!std::strcmp(key, "conv_l2hint")) h->tune.conv_l2hint = value;
     else if (!std::strcmp(key, "conv_lanes")) h->tune.conv_lanes = value;
     else return fail(h, SSPYR_ERR_ARG, std::string("unknown tuning key ") + key);

@@ -78,7 +78,6 @@ struct Tuning {
                                // 1 = for frames of >= 4 Mpixel, 2 = always, 0 = never (one launch per level, conv_march.cuh,
                                // which is also the only path for row bands)
     int conv_casc_seg = 0;     // cascade: segment height in rows (0 = automatic, cascade_seg_rows)
-    int conv_casc_debug = 0;   // cascade timing experiments (WRONG results): 1 no per-step waits, 2 no per-step publishes, 4 no start waits
     int conv_band_lanes = 6;   // CONV row bands over peer memory: builds of different slots in flight (<= frame slots; measured on
                                // 8 GPUs, 8K / 16K: 3 -> 2.9x / 6.1x, 6 -> 3.6x / 6.8x, 8 -> 3.7x / 6.7x of one GPU, profiles/r2_bands.md)
     int conv_band_chain = 0;   // CONV row bands over peer memory: chain levels across the band seam through the neighbours'

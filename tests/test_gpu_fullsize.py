@@ -85,7 +85,7 @@ def test_c3_as_specified_256_frames_through_the_ring(pkg, O, synth):
     try:
         dims = [ring.level_dims(o) for o in range(octs)]
 
-        def checksum(ss, slot):                   # xor-fold of the raw bits of the in-place tail of every octave
+        def checksum(ss, slot):                   # octave-weighted sum of the raw bits of the in-place tail of every octave
             acc = torch.zeros((), dtype=torch.int64, device=dev)
             for o, (r, c, p) in enumerate(dims):
                 ptr = ss.device_ptr(o, 0, pkg.KIND_INPLACE, frame=slot)
