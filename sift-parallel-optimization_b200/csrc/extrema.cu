@@ -2,14 +2,18 @@
 // after the pyramid; the reference stops at DoG, GuassDePyramid.h:136-149).  Both modes.
 //
 // One launch per frame covers every octave.  A CTA owns a 64 x 16 pixel tile and walks up the S+2 DoG planes of its
-// octave with a three-plane ring in shared memory: plane s+1's tile (+ 1-pixel halo) is loaded while planes s-1, s are
-// still resident, so every DoG plane is read from HBM/L2 ONCE (x1.16 halo), 128-bit loads on the aligned interior.
+// octave with a four-plane ring in shared memory filled by cp.async: the tile (+ 1-pixel halo) of plane s+2 is in flight
+// while level s is scanned out of planes s-1, s, s+1, so every DoG plane is read from HBM/L2 ONCE (x1.16 halo, 16-byte
+// copies on the aligned interior) and the loads hide behind the comparisons (the first version loaded, synchronised and
+// scanned in turn: long-scoreboard and barrier stalls, 1.7 TB/s; profiles/r2_extrema_c2_ncu_full.txt).
 // Results, either or both:
 //   * SSPYR_OUT_KEYPOINTS: a compacted list of (x, y, octave, level, value) records per frame slot -- warp-aggregated
 //     reservation (one atomicAdd per warp and row) behind a per-slot cursor.  A 1080p pyramid is 66 MB of planes; its
 //     keypoints are kilobytes: this is what takes the end-to-end path off the PCIe link.
 //   * SSPYR_OUT_EXTREMA: one flag byte per pixel and level (the round-1 output, kept for the tests' exact comparison
 //     with the oracle scan).
+#include <cuda_pipeline_primitives.h>
+
 #include "sspyr_internal.h"
 
 namespace sspyr {
@@ -40,33 +44,33 @@ struct ExtParams {
     float thresh;
 };
 
-// plane tile (+ halo, coordinates clamped into the plane: border pixels are never tested, their halo is never used)
+// plane tile (+ halo, coordinates clamped into the plane: border pixels are never tested, their halo is never used),
+// asynchronously: 16-byte cp.async on the aligned interior of full-width tiles, 4-byte cp.async for the rest
 __device__ __forceinline__ void load_tile(float* __restrict__ s, const float* __restrict__ plane, int H, int W, int pitch,
                                           int x0, int y0, int tid) {
-    // interior columns: 16 float4 per row when the whole 64-column span exists
     const bool full = x0 + EXT_TW <= W;
     for (int i = tid; i < EXT_ROWS * (EXT_TW / 4); i += EXT_THREADS) {
         const int r = i / (EXT_TW / 4), q = i - r * (EXT_TW / 4);
         const int gy = min(max(y0 - 1 + r, 0), H - 1);
         float* d = s + r * EXT_PITCH + 4 + 4 * q;
         if (full) {
-            *reinterpret_cast<float4*>(d) = __ldcs(reinterpret_cast<const float4*>(plane + (size_t)gy * pitch + x0) + q);
+            __pipeline_memcpy_async(d, plane + (size_t)gy * pitch + x0 + 4 * q, 16);
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) d[k] = __ldcs(plane + (size_t)gy * pitch + min(x0 + 4 * q + k, W - 1));
+            for (int k = 0; k < 4; ++k) __pipeline_memcpy_async(d + k, plane + (size_t)gy * pitch + min(x0 + 4 * q + k, W - 1), 4);
         }
     }
     for (int i = tid; i < EXT_ROWS * 2; i += EXT_THREADS) {       // the two halo columns
         const int r = i >> 1, side = i & 1;
         const int gy = min(max(y0 - 1 + r, 0), H - 1);
         const int gx = side ? min(x0 + EXT_TW, W - 1) : max(x0 - 1, 0);
-        s[r * EXT_PITCH + (side ? 4 + EXT_TW : 3)] = __ldcs(plane + (size_t)gy * pitch + gx);
+        __pipeline_memcpy_async(s + r * EXT_PITCH + (side ? 4 + EXT_TW : 3), plane + (size_t)gy * pitch + gx, 4);
     }
 }
 
 __global__ void __launch_bounds__(EXT_THREADS)
 extrema_tile_kernel(const __grid_constant__ ExtParams P) {
-    __shared__ __align__(16) float ring[3][EXT_ROWS * EXT_PITCH];
+    __shared__ __align__(16) float ring[4][EXT_ROWS * EXT_PITCH];
     const unsigned fz = blockIdx.x / P.tiles_per_frame;
     unsigned t = blockIdx.x - fz * P.tiles_per_frame;
     int o = 0;
@@ -81,14 +85,20 @@ extrema_tile_kernel(const __grid_constant__ ExtParams P) {
     unsigned* kp_head = P.kp ? reinterpret_cast<unsigned*>(P.kp + (size_t)fz * P.kp_frame_stride) : nullptr;
     int4* kp_rec = kp_head ? reinterpret_cast<int4*>(kp_head + 4) : nullptr;
 
-    load_tile(ring[0], dog, O.H, O.W, O.pitch, x0, y0, tid);
-    load_tile(ring[1], dog + O.plane, O.H, O.W, O.pitch, x0, y0, tid);
+    // planes 0, 1, 2 start moving now (one cp.async group each); inside the loop plane s+2 is issued before level s is
+    // scanned and the wait leaves that newest group in flight
+    for (int q = 0; q < 3 && q <= P.S + 1; ++q) {
+        load_tile(ring[q], dog + (size_t)q * O.plane, O.H, O.W, O.pitch, x0, y0, tid);
+        __pipeline_commit();
+    }
     for (int s = 1; s <= P.S; ++s) {
-        load_tile(ring[(s + 1) % 3], dog + (size_t)(s + 1) * O.plane, O.H, O.W, O.pitch, x0, y0, tid);
+        if (s + 2 <= P.S + 1) load_tile(ring[(s + 2) & 3], dog + (size_t)(s + 2) * O.plane, O.H, O.W, O.pitch, x0, y0, tid);
+        __pipeline_commit();                                      // (an empty group when there is no plane s+2: keeps the count)
+        __pipeline_wait_prior(1);                                 // planes <= s+1 have landed
         __syncthreads();
-        const float* lo = ring[(s - 1) % 3];
-        const float* mid = ring[s % 3];
-        const float* hi = ring[(s + 1) % 3];
+        const float* lo = ring[(s - 1) & 3];
+        const float* mid = ring[s & 3];
+        const float* hi = ring[(s + 1) & 3];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int r = ry + j, gy = y0 + r, gx = x0 + cx;
@@ -134,7 +144,7 @@ extrema_tile_kernel(const __grid_constant__ ExtParams P) {
                 }
             }
         }
-        __syncthreads();                                          // ring slot (s - 1) % 3 is loaded next
+        __syncthreads();                                          // ring slot (s - 1) & 3 receives plane s + 3 in the next iteration
     }
 }
 
