@@ -49,6 +49,8 @@ WORKLOADS = {
     "c3": (2160, 3840, 5, 256, "batch", "3840x2160 batch of 256 frames, 5 octaves x 6 levels, frames sharded per GPU"),
     "c4": (4320, 7680, 5, 1, "rowband", "7680x4320 single image, 5 octaves x 6 levels, row bands per GPU"),
     "c5": (16384, 16384, 8, 1, "rowband", "16384x16384 image, 8 octaves x 6 levels, row bands per GPU"),
+    # tuning aid, not a BASELINE config: one 8-GPU band of C4 as a stand-alone frame (segment-height sweeps on one GPU)
+    "c4band": (544, 7680, 5, 1, "replica", "7680x544: the geometry of one of 8 row bands of C4, as a stand-alone frame"),
 }
 S = 3
 L2_BYTES = 126 << 20
@@ -226,7 +228,7 @@ def rank_geometry(pkg, wl: str, world: int, rank: int):
     return H, 0, H, W, octs, frames
 
 
-DEFAULT_STEPS = {"c1": (300, 20), "c2": (2000, 50), "c3": (3, 3), "c4": (200, 10), "c5": (30, 3)}
+DEFAULT_STEPS = {"c1": (300, 20), "c2": (2000, 50), "c3": (3, 3), "c4": (200, 10), "c5": (30, 3), "c4band": (600, 30)}
 _noise_cache: dict = {}
 
 
