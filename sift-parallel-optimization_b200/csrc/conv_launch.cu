@@ -250,7 +250,6 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
             P.seg_dep = lv0 + (size_t)(level - 1) * h->seg_cap[octave];
             chained_dep = true;
             const int Rl = h->conv[level].radius;
-            const int strips = (g.W + CONV_TW - 1) / CONV_TW;
             if (h->peer[0].attached) {                        // the band above: the segment rows that hold its last R rows
                 const sspyr_ctx::Peer& q = h->peer[0];
                 const int nrows = march_seg_rows(q.H[octave], g.W, count, sms, h->tune.conv_waves, conv_seg_min_rows(h));
@@ -258,7 +257,6 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
                 P.peer_up_nsegs = (q.H[octave] + nrows - 1) / nrows;
                 P.peer_up_first = std::max(0, (q.H[octave] - Rl) / nrows);
                 if (P.peer_up_nsegs - P.peer_up_first > 2) P.peer_up_first = P.peer_up_nsegs - 2;   // (32-row segments, R <= 12: two rows at most)
-                (void)strips;
             }
             if (h->peer[1].attached) {                        // the band below: its first segment row holds its first R rows
                 const sspyr_ctx::Peer& q = h->peer[1];
