@@ -139,8 +139,10 @@ bool make_plane_tensor_map(CUtensorMap* map, const float* plane0, int pitch, int
 // segment pays 2R warm-up rows and one exposed load, so 96-row segments (3 steps) beat 32-row ones by 1.4x on band-sized
 // and 1080p planes (profiles/r2_bands.md).  A single-slot handle builds one pyramid at a time: 32-row segments, the
 // shortest critical path.  An explicit conv_seg_min always wins.
-static int conv_seg_min_rows(const sspyr_ctx* h) {
+static int conv_seg_min_rows(const sspyr_ctx* h, int count) {
     if (h->tune.conv_seg_min > 0) return h->tune.conv_seg_min;
+    if (count > 1) return 32;                             // a batched launch fills the GPU by itself (1080p x 8 frames: 96-row
+                                                          // segments measured 14 % slower than 32-row ones)
     const bool banded = h->cfg.full_height != h->cfg.height;
     const int lanes = banded ? h->tune.conv_band_lanes : h->tune.conv_lanes;
     return (h->cfg.frames > 1 && lanes > 1 && !h->tune.timing) ? 96 : 32;
@@ -227,7 +229,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
     // radii above 12 and conv_march = 0 use the one-tile-per-CTA kernel.
     const bool march = level_marches(h, level);
     const bool peered_any = h->peer[0].attached || h->peer[1].attached;
-    const int seg_rows = march_seg_rows(g.H, g.W, count, sms, h->tune.conv_waves, conv_seg_min_rows(h));
+    const int seg_rows = march_seg_rows(g.H, g.W, count, sms, h->tune.conv_waves, conv_seg_min_rows(h, count));
     const long long ctas = march_ctas(g.H, g.W, count, seg_rows);
     // Level chaining (whole-pyramid builds): the strip kernels of one octave count finished segments; a level whose
     // source plane was produced by a chained strip kernel of the same octave (same grid) waits per segment instead of
@@ -252,7 +254,7 @@ cudaError_t launch_conv_step(const sspyr_ctx* h, int first, int count, int octav
             const int Rl = h->conv[level].radius;
             if (h->peer[0].attached) {                        // the band above: the segment rows that hold its last R rows
                 const sspyr_ctx::Peer& q = h->peer[0];
-                const int nrows = march_seg_rows(q.H[octave], g.W, count, sms, h->tune.conv_waves, conv_seg_min_rows(h));
+                const int nrows = march_seg_rows(q.H[octave], g.W, count, sms, h->tune.conv_waves, conv_seg_min_rows(h, count));
                 P.peer_seg_up = q.seg + (size_t)first * q.seg_frame_stride + q.seg_off[octave] + (size_t)(level - 1) * q.seg_cap[octave];
                 P.peer_up_nsegs = (q.H[octave] + nrows - 1) / nrows;
                 P.peer_up_first = std::max(0, (q.H[octave] - Rl) / nrows);
