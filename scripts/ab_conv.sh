@@ -1,7 +1,7 @@
 #!/bin/bash
 # scripts/ab_conv.sh -- A/B of CONV kernel builds in one gpurun call: the shipped libsspyr.so against every evaluation
 # build build/libsspyr_<tag>.so (see csrc/Makefile), same bench lines; the conv GPU tests run on every build first.
-#   make -C sift-parallel-optimization_b200/csrc -j8 OUT=$PWD/build/libsspyr_colpass2.so OBJ=$PWD/build/csrc_colpass2 EXTRA=-DSSPYR_STRIP_COLPASS=2
+#   make -C sift-parallel-optimization_b200/csrc -j8 OUT=$PWD/build/libsspyr_<tag>.so OBJ=$PWD/build/csrc_<tag> EXTRA=-D<MACRO>=<value>
 #   gpurun -- 'WLS="c4 c5 c3" bash scripts/ab_conv.sh'
 set -u
 mkdir -p gpurun_out
