@@ -45,3 +45,17 @@ def test_extras_tables_name_known_workloads():
     for key, wl, mode, steps, warm in bench.EXTRAS_NX:
         assert bench.WORKLOADS[wl][4] in ("rowband", "batch") and warm >= 3
     assert bench.WORKLOADS["c3"][3] == 256 and bench.parse_args.__module__ == "bench"
+
+
+def test_host_side_helpers_never_break_a_run():
+    """bind_to_gpu_numa_node reports what it finds and never raises (here: no GPU at all); Solo offers every method of
+    Dist that measure() / run_e2e() call, so a one-rank measurement inside an N-rank job takes the same code path."""
+    sys.path.insert(0, ROOT)
+    import bench
+    info = bench.bind_to_gpu_numa_node(0)
+    assert isinstance(info, dict) and "numa_node" in info
+    solo = bench.Solo()
+    for name in ("barrier", "max", "sum", "gather"):
+        assert callable(getattr(solo, name)) and callable(getattr(bench.Dist, name))
+    assert solo.max(3.5) == 3.5 and solo.sum(2.0) == 2.0 and solo.gather(1.25) == [1.25] and solo.world == 1
+    assert bench.square_equivalent(2160, 3840) == 2880 == bench.REF_SIDE_CAP          # c3's reference arm runs at full size
